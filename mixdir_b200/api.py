@@ -1,0 +1,125 @@
+"""Python mirror of the reference's user entry points, on top of the CUDA engine.
+
+  mixdir()   <->  /root/reference/R/mixdir.R:79-138
+  predict()  <->  /root/reference/R/predict.R:29-105
+
+R is not available in this image, so this module plays the role of the R adapter
+(r_adapter/ holds the Rcpp/R sources a maintainer would add):
+same argument names, defaults, result fields, errors and warnings.  All numeric
+work happens in the C-ABI library; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _capi
+from .coding import code_columns, recode_for_predict
+from .engine import WARN_DP_TEXT, WARN_ELBO_TEXT, Engine
+
+
+def _as_columns(X):
+    """data.frame-like input -> (names, list of columns)."""
+    if hasattr(X, "columns") and hasattr(X, "__getitem__") and not isinstance(X, np.ndarray):
+        names = [str(c) for c in X.columns]
+        return names, [list(X[c]) for c in X.columns]
+    if isinstance(X, dict):
+        names = list(X.keys())
+        cols = [list(v) if isinstance(v, (list, tuple, np.ndarray)) else [v] for v in X.values()]
+        return names, cols
+    A = np.asarray(X, dtype=object)
+    if A.ndim == 1:
+        A = A.reshape(1, -1)
+    names = [f"V{j + 1}" for j in range(A.shape[1])]
+    return names, [list(A[:, j]) for j in range(A.shape[1])]
+
+
+def default_inits(n_rows, ncat, n_latent, rng):
+    """The reference's random initial values (R/mixdir_vi.R:28-39): zeta_init ~ Dirichlet(1)
+    rows, phi_init in {1,2,3}.  R's RNG stream is not reproducible outside R; parity tests
+    pass explicit inits instead."""
+    zeta = rng.dirichlet(np.ones(n_latent), size=n_rows)
+    phi = rng.integers(1, 4, size=int(n_latent * np.sum(ncat))).astype(np.float64)
+    return zeta, phi
+
+
+def mixdir(X, n_latent=3, alpha=None, beta=None, select_latent=False, max_iter=100, epsilon=1e-3,
+           na_handle="ignore", repetitions=1, zeta_init=None, phi_init=None, seed=None,
+           devices=None, verbose=False):
+    """Cluster categorical data; returns a dict with the reference's result fields
+    (converged, convergence, ELBO, lambda, pred_class, class_prob, category_prob,
+    specific_params, na_handle) -- R/mixdir.R:79-138, R/mixdir_vi.R:143-155."""
+    names, cols = _as_columns(X)
+    codes, categories = code_columns(cols, na_handle=na_handle)
+    ncat = np.array([len(c) for c in categories], dtype=np.int32)
+    n_rows = codes.shape[0]
+    rng = np.random.default_rng(seed)
+    K = int(n_latent)
+    best = None
+    with Engine(codes, ncat, devices=devices) as eng:
+        for _rep in range(int(repetitions)):  # R/mixdir.R:120-134
+            z0, p0 = default_inits(n_rows, ncat, K, rng)
+            if zeta_init is not None:
+                z0 = np.asarray(zeta_init, dtype=float)
+            if phi_init is not None:
+                p0 = np.asarray(phi_init, dtype=float)
+            res = eng.fit(K, z0.sum(axis=0), p0, dp=bool(select_latent), alpha=alpha, beta=beta,
+                          max_iter=max_iter, epsilon=epsilon)
+            if res["warn_flags"] & _capi.WARN_ELBO_DECREASED:
+                warnings.warn(WARN_ELBO_TEXT)
+            if res["warn_flags"] & _capi.WARN_DP_LAST_COMPONENT:
+                warnings.warn(WARN_DP_TEXT)
+            if verbose:
+                for i, e in enumerate(res["convergence"], 1):
+                    if i % 10 == 0:  # R/mixdir_vi.R:111
+                        print(f"Iter: {i} ELBO: {e:.4g}")
+            if best is None or best["ELBO"] < res["ELBO"]:
+                best = res
+    return _as_result(best, names, categories, K, bool(select_latent), na_handle)
+
+
+def _ragged_to_lists(flat, categories, K):
+    """ragged (j,k,r) -> list[J] of list[K] of dict(level -> value) (named vectors in R)."""
+    out, o = [], 0
+    for cats in categories:
+        c = len(cats)
+        out.append([dict(zip(cats, flat[o + k * c:o + (k + 1) * c])) for k in range(K)])
+        o += K * c
+    return out
+
+
+def _as_result(res, names, categories, K, dp, na_handle):
+    cat_prob = dict(zip(names, _ragged_to_lists(res["category_prob"], categories, K)))
+    phi = _ragged_to_lists(res["phi"], categories, K)
+    spec = dict(kappa1=res["kappa1"], kappa2=res["kappa2"], phi=phi) if dp else \
+        dict(omega=res["omega"], phi=phi)
+    return {
+        "converged": res["converged"], "convergence": res["convergence"], "ELBO": res["ELBO"],
+        "lambda": res["lambda_"], "pred_class": res["pred_class"], "class_prob": res["class_prob"],
+        "category_prob": cat_prob, "specific_params": spec, "na_handle": na_handle,
+        "_names": names, "_categories": categories, "_U_flat": res["category_prob"],
+    }
+
+
+def predict(obj, newdata=None):
+    """predict.mixdir (R/predict.R:29-36): class_prob of the training data, or the posterior
+    class probabilities of new rows under (lambda, category_prob)."""
+    if newdata is None:
+        return obj["class_prob"]
+    names, categories = obj["_names"], obj["_categories"]
+    nd_names, nd_cols = _as_columns(newdata)
+    by_name = dict(zip(nd_names, nd_cols))
+    for n in nd_names:
+        if n not in names:  # stop() of R/predict.R:95-96
+            raise ValueError(f"The new observation X contains a category {n} not in the data")
+    codes, unseen = recode_for_predict(by_name, names, categories, obj.get("na_handle") or "ignore")
+    for col, vals in unseen.items():  # warning() of R/predict.R:75-80
+        lst = ",".join(f'"{v}"' for v in sorted(vals))
+        warnings.warn(f'The new data has a response ({lst}) for category "{col}" which is not in '
+                      "category_prob. Handling X[j, i] it as if it was missing.\n")
+    ncat = np.array([len(c) for c in categories], dtype=np.int32)
+    K = len(obj["lambda"])
+    with Engine(codes, ncat) as eng:
+        cp, _ = eng.predict(K, obj["lambda"], obj["_U_flat"], want_pred_class=False)
+    return cp

@@ -1,0 +1,1075 @@
+// mixdir_b200 host engine + C ABI (include/mixdir_b200.h).
+//
+// Drives the coordinate-ascent loop of mixdir_vi() (/root/reference/R/mixdir_vi.R:58-115)
+// and mixdir_vi_dp() (/root/reference/R/mixdir_vi_dp.R:66-129) entirely on the GPU(s):
+// per iteration  prior step -> fused E+M pass -> deterministic partial reduction ->
+// [NCCL all-reduce of the statistics buffer] -> parameter/ELBO step -> convergence test,
+// with one 32-byte status read-back.  No CPU fallback: every entry point fails with
+// MIXDIR_B200_CUDA_ERROR if no usable device is present.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mixdir_b200.h"
+#include "kernels.cuh"
+
+using namespace mxd;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      char _b[512];                                                                        \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+               __FILE__, __LINE__);                                                        \
+      return fail(MIXDIR_B200_CUDA_ERROR, _b);                                             \
+    }                                                                                      \
+  } while (0)
+
+#define RET_IF(expr)                   \
+  do {                                 \
+    int _s = (expr);                   \
+    if (_s != MIXDIR_B200_OK) return _s; \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (torch's bundled libnccl.so.2 if it is already in
+// the process, else the system one) so the library loads on machines without it.
+// ---------------------------------------------------------------------------
+namespace nccl {
+typedef struct ncclComm* comm_t;
+struct unique_id { char internal[128]; };
+enum { kSum = 0, kMax = 2 };
+enum { kInt64 = 4, kDouble = 8 };  // ncclInt64 = 4, ncclFloat64 = 8 (nccl.h)
+typedef int (*GetUniqueId_t)(unique_id*);
+typedef int (*CommInitRank_t)(comm_t*, int, unique_id, int);
+typedef int (*CommInitAll_t)(comm_t*, int, const int*);
+typedef int (*CommDestroy_t)(comm_t);
+typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, comm_t, cudaStream_t);
+typedef int (*Group_t)(void);
+typedef const char* (*GetErrorString_t)(int);
+static void* lib = nullptr;
+static GetUniqueId_t GetUniqueId;
+static CommInitRank_t CommInitRank;
+static CommInitAll_t CommInitAll;
+static CommDestroy_t CommDestroy;
+static AllReduce_t AllReduce;
+static Group_t GroupStart, GroupEnd;
+static GetErrorString_t GetErrorString;
+
+static int load() {
+  if (lib) return MIXDIR_B200_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(MIXDIR_B200_CUDA_ERROR, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define SYM(name)                                                                      \
+  name = (name##_t)dlsym(h, "nccl" #name);                                             \
+  if (!name) return fail(MIXDIR_B200_CUDA_ERROR, "libnccl lacks nccl" #name);
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommInitAll) SYM(CommDestroy) SYM(AllReduce)
+  SYM(GetErrorString)
+#undef SYM
+  GroupStart = (Group_t)dlsym(h, "ncclGroupStart");
+  GroupEnd = (Group_t)dlsym(h, "ncclGroupEnd");
+  if (!GroupStart || !GroupEnd) return fail(MIXDIR_B200_CUDA_ERROR, "libnccl lacks ncclGroup*");
+  lib = h;
+  return MIXDIR_B200_OK;
+}
+}  // namespace nccl
+
+#define NCCL_TRY(expr)                                                                    \
+  do {                                                                                    \
+    int _r = (expr);                                                                      \
+    if (_r != 0) {                                                                        \
+      char _b[512];                                                                       \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, nccl::GetErrorString(_r),   \
+               __FILE__, __LINE__);                                                       \
+      return fail(MIXDIR_B200_CUDA_ERROR, _b);                                            \
+    }                                                                                     \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct Plan {
+  int engine = 0;  // 1 generic, 2 fused
+  int KP = 0;
+  int KC = 0, P = 1, RG = 8, W = 0;
+  int n_clusters = 0;
+  size_t smem = 0;
+  int R = 0;  // rows per tile
+};
+
+struct Shard {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t row0 = 0, n_rows = 0;
+  uint8_t* d_codes = nullptr;
+  int* d_ncat = nullptr;
+  int* d_rowoff = nullptr;
+  int* d_rowoff_pad = nullptr;
+  int64_t* d_ragoff = nullptr;
+  uint8_t* d_na_row = nullptr;
+  nccl::comm_t comm = nullptr;
+  int sm_count = 0, smem_optin = 0;
+  // workspace (sized for ws_K / ws_KP)
+  int ws_K = 0, ws_KP = 0, ws_iter = 0, ws_clusters = 0, ws_ctas = 0;
+  double *d_T = nullptr, *d_phi = nullptr, *d_logU = nullptr, *d_stats = nullptr;
+  double *d_logprior = nullptr, *d_cs_a = nullptr, *d_cs_b = nullptr, *d_pieces = nullptr;
+  double *d_trace = nullptr, *d_rag_a = nullptr, *d_rag_b = nullptr, *d_lambda = nullptr;
+  double *d_lambda_pad = nullptr, *d_prior_out = nullptr;
+  double *d_Spart = nullptr, *d_cspart = nullptr, *d_Hpart = nullptr;
+  int *d_perm = nullptr, *d_underflow = nullptr, *d_warn = nullptr;
+  PriorState* d_prior = nullptr;
+  IterStatus* d_status = nullptr;
+  IterStatus* h_status = nullptr;  // pinned
+  cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
+  std::vector<cudaEvent_t> ev_em;
+};
+
+struct mixdir_b200_handle {
+  int J = 0, CB = 1, row_bytes = 0, WPR = 0, NR = 0;
+  int64_t n_rows = 0;        // rows held by this handle (all shards)
+  int64_t n_missing = 0;     // global
+  int max_code = 0;          // global
+  int64_t sum_ncat = 0;
+  std::vector<int> ncat, rowoff, rowoff_pad;
+  std::vector<int64_t> ragoff1;  // ragged offsets for K = 1 (scaled by K at use)
+  std::vector<Shard> shards;
+  int rank = 0, world = 1;   // multi-process flavour
+  int engine_pref = 0;
+  mixdir_b200_timing timing = {};
+};
+
+static bool needs_allreduce(const mixdir_b200_handle* h) {
+  return h->world > 1 || h->shards.size() > 1;
+}
+
+// all-reduce `count` doubles/int64 in place on every shard's stream
+static int allreduce(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t count, int dtype,
+                     int op) {
+  if (!needs_allreduce(h)) return MIXDIR_B200_OK;
+  NCCL_TRY(nccl::GroupStart());
+  for (size_t s = 0; s < h->shards.size(); s++) {
+    Shard& sh = h->shards[s];
+    int r = nccl::AllReduce(bufs[s], bufs[s], count, dtype, op, sh.comm, sh.stream);
+    if (r != 0) {
+      nccl::GroupEnd();
+      return fail(MIXDIR_B200_CUDA_ERROR, std::string("ncclAllReduce: ") + nccl::GetErrorString(r));
+    }
+  }
+  NCCL_TRY(nccl::GroupEnd());
+  return MIXDIR_B200_OK;
+}
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+  CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return MIXDIR_B200_OK;
+}
+template <typename T>
+static void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static void free_workspace(Shard& s) {
+  dfree(s.d_T); dfree(s.d_phi); dfree(s.d_logU); dfree(s.d_stats); dfree(s.d_logprior);
+  dfree(s.d_cs_a); dfree(s.d_cs_b); dfree(s.d_pieces); dfree(s.d_trace); dfree(s.d_rag_a);
+  dfree(s.d_rag_b); dfree(s.d_lambda); dfree(s.d_lambda_pad); dfree(s.d_prior_out);
+  dfree(s.d_Spart); dfree(s.d_cspart); dfree(s.d_Hpart); dfree(s.d_perm);
+  dfree(s.d_underflow); dfree(s.d_warn); dfree(s.d_prior); dfree(s.d_status);
+  s.ws_K = s.ws_KP = s.ws_iter = s.ws_clusters = s.ws_ctas = 0;
+}
+
+static void free_shard(Shard& s) {
+  cudaSetDevice(s.device);
+  free_workspace(s);
+  dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
+  dfree(s.d_ragoff); dfree(s.d_na_row);
+  if (s.h_status) cudaFreeHost(s.h_status);
+  s.h_status = nullptr;
+  for (auto e : s.ev_em) cudaEventDestroy(e);
+  s.ev_em.clear();
+  if (s.ev_loop0) cudaEventDestroy(s.ev_loop0);
+  if (s.ev_loop1) cudaEventDestroy(s.ev_loop1);
+  s.ev_loop0 = s.ev_loop1 = nullptr;
+  if (s.comm && nccl::lib) nccl::CommDestroy(s.comm);
+  s.comm = nullptr;
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s.stream = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// create
+// ---------------------------------------------------------------------------
+static int init_geometry(mixdir_b200_handle* h, int code_bytes, int J, const int* ncat) {
+  if (code_bytes != 1 && code_bytes != 2) return fail(MIXDIR_B200_BAD_ARGUMENT, "code_bytes must be 1 or 2");
+  if (J < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_features must be >= 1");
+  if (!ncat) return fail(MIXDIR_B200_BAD_ARGUMENT, "ncat is NULL");
+  h->J = J;
+  h->CB = code_bytes;
+  h->row_bytes = (J * code_bytes + 3) & ~3;
+  h->WPR = h->row_bytes / 4;
+  h->ncat.assign(ncat, ncat + J);
+  h->rowoff.resize(J);
+  h->ragoff1.resize(J);
+  int nr = 0;
+  int64_t ro = 0;
+  const int limit = code_bytes == 1 ? 255 : 65535;
+  for (int j = 0; j < J; j++) {
+    // mixdir() stops on a column without levels (R/mixdir.R:112-115)
+    if (ncat[j] < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "a feature has no categories (ncat[j] < 1)");
+    if (ncat[j] > limit) return fail(MIXDIR_B200_BAD_ARGUMENT, "ncat[j] does not fit code_bytes");
+    h->rowoff[j] = nr;
+    nr += ncat[j] + 1;
+    h->ragoff1[j] = ro;
+    ro += ncat[j];
+  }
+  h->NR = nr;
+  h->sum_ncat = ro;
+  const int fpw = 4 / code_bytes;
+  h->rowoff_pad.assign((size_t)h->WPR * fpw, h->rowoff[0]);  // padding features -> NA row of feature 0
+  for (int j = 0; j < J; j++) h->rowoff_pad[j] = h->rowoff[j];
+  return MIXDIR_B200_OK;
+}
+
+static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
+  CU_TRY(cudaSetDevice(s.device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, s.device));
+  if (prop.major < 9)
+    return fail(MIXDIR_B200_CUDA_ERROR, "mixdir_b200 needs a Blackwell-class GPU (built for sm_100a)");
+  s.sm_count = prop.multiProcessorCount;
+  s.smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&s.ev_loop0));
+  CU_TRY(cudaEventCreate(&s.ev_loop1));
+  CU_TRY(cudaMallocHost((void**)&s.h_status, sizeof(IterStatus)));
+  const int J = h->J;
+  RET_IF(dalloc(&s.d_ncat, J));
+  RET_IF(dalloc(&s.d_rowoff, J));
+  RET_IF(dalloc(&s.d_rowoff_pad, h->rowoff_pad.size()));
+  RET_IF(dalloc(&s.d_ragoff, J));
+  RET_IF(dalloc(&s.d_na_row, h->NR));
+  std::vector<uint8_t> na(h->NR, 0);
+  for (int j = 0; j < J; j++) na[h->rowoff[j]] = 1;
+  CU_TRY(cudaMemcpy(s.d_ncat, h->ncat.data(), J * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(s.d_rowoff, h->rowoff.data(), J * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(s.d_rowoff_pad, h->rowoff_pad.data(), h->rowoff_pad.size() * sizeof(int),
+                    cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(s.d_na_row, na.data(), h->NR, cudaMemcpyHostToDevice));
+  const size_t bytes = (size_t)(s.n_rows + kRowPad) * h->row_bytes;
+  RET_IF(dalloc(&s.d_codes, bytes));
+  CU_TRY(cudaMemsetAsync(s.d_codes, 0, bytes, s.stream));
+  return MIXDIR_B200_OK;
+}
+
+// scan the uploaded codes: NA count, largest code, validity
+static int scan_codes(mixdir_b200_handle* h) {
+  std::vector<ScanOut*> d_out(h->shards.size(), nullptr);
+  int64_t miss = 0;
+  int mx = 0, bad = 0;
+  for (size_t i = 0; i < h->shards.size(); i++) {
+    Shard& s = h->shards[i];
+    CU_TRY(cudaSetDevice(s.device));
+    RET_IF(dalloc(&d_out[i], 1));
+    CU_TRY(cudaMemsetAsync(d_out[i], 0, sizeof(ScanOut), s.stream));
+    if (s.n_rows > 0) {
+      const int grid = s.sm_count * 8;
+      if (h->CB == 1)
+        k_scan_codes<1><<<grid, 256, 0, s.stream>>>(s.d_codes, h->row_bytes, s.n_rows, h->J, s.d_ncat, d_out[i]);
+      else
+        k_scan_codes<2><<<grid, 256, 0, s.stream>>>(s.d_codes, h->row_bytes, s.n_rows, h->J, s.d_ncat, d_out[i]);
+      CU_TRY(cudaGetLastError());
+    }
+  }
+  for (size_t i = 0; i < h->shards.size(); i++) {
+    Shard& s = h->shards[i];
+    CU_TRY(cudaSetDevice(s.device));
+    ScanOut o;
+    CU_TRY(cudaMemcpyAsync(&o, d_out[i], sizeof o, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    cudaFree(d_out[i]);
+    miss += (int64_t)o.n_missing;
+    mx = std::max(mx, o.max_code);
+    bad |= o.bad;
+  }
+  if (h->world > 1) {  // combine over ranks (multi-process flavour: one shard)
+    Shard& s = h->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    long long* d = nullptr;
+    RET_IF(dalloc(&d, 3));
+    long long v[3] = {(long long)miss, (long long)mx, (long long)bad};
+    CU_TRY(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, s.stream));
+    NCCL_TRY(nccl::AllReduce(d, d, 1, nccl::kInt64, nccl::kSum, s.comm, s.stream));
+    NCCL_TRY(nccl::AllReduce(d + 1, d + 1, 2, nccl::kInt64, nccl::kMax, s.comm, s.stream));
+    CU_TRY(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    cudaFree(d);
+    miss = v[0];
+    mx = (int)v[1];
+    bad = (int)v[2];
+  }
+  if (bad) return fail(MIXDIR_B200_BAD_ARGUMENT, "a code exceeds its feature's number of categories");
+  h->n_missing = miss;
+  h->max_code = mx;
+  return MIXDIR_B200_OK;
+}
+
+static int upload_codes(mixdir_b200_handle* h, Shard& s, const uint8_t* src_rows) {
+  if (s.n_rows == 0) return MIXDIR_B200_OK;
+  const size_t w = (size_t)h->J * h->CB;
+  if ((int)w == h->row_bytes)
+    CU_TRY(cudaMemcpyAsync(s.d_codes, src_rows, w * s.n_rows, cudaMemcpyHostToDevice, s.stream));
+  else
+    CU_TRY(cudaMemcpy2DAsync(s.d_codes, h->row_bytes, src_rows, w, w, s.n_rows,
+                             cudaMemcpyHostToDevice, s.stream));
+  return MIXDIR_B200_OK;
+}
+
+static int make_shards(mixdir_b200_handle* h, int64_t n_rows, int n_devices, const int* device_ids) {
+  int ndev = n_devices <= 0 ? 1 : n_devices;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(MIXDIR_B200_CUDA_ERROR, "no CUDA device available (mixdir_b200 has no CPU path)");
+  if (ndev > count && !device_ids) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_devices exceeds the visible GPUs");
+  h->n_rows = n_rows;
+  h->shards.resize(ndev);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < ndev; d++) {
+    Shard& s = h->shards[d];
+    s.device = device_ids ? device_ids[d] : (ndev == 1 ? cur : d);
+    s.row0 = n_rows * d / ndev;  // contiguous row blocks
+    s.n_rows = n_rows * (d + 1) / ndev - s.row0;
+  }
+  if (ndev > 1) {
+    RET_IF(nccl::load());
+    std::vector<nccl::comm_t> comms(ndev);
+    std::vector<int> devs(ndev);
+    for (int d = 0; d < ndev; d++) devs[d] = h->shards[d].device;
+    NCCL_TRY(nccl::CommInitAll(comms.data(), ndev, devs.data()));
+    for (int d = 0; d < ndev; d++) h->shards[d].comm = comms[d];
+  }
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_destroy(mixdir_b200_handle* h) {
+  if (!h) return MIXDIR_B200_OK;
+  for (auto& s : h->shards) free_shard(s);
+  delete h;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_create(const void* codes, int code_bytes, int64_t n_rows, int n_features,
+                                  const int* ncat, int n_devices, const int* device_ids,
+                                  mixdir_b200_handle** out) {
+  if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (n_rows < 0 || (n_rows > 0 && !codes)) return fail(MIXDIR_B200_BAD_ARGUMENT, "codes is NULL");
+  mixdir_b200_handle* h = new mixdir_b200_handle();
+  int st = init_geometry(h, code_bytes, n_features, ncat);
+  if (st == MIXDIR_B200_OK) st = make_shards(h, n_rows, n_devices, device_ids);
+  for (size_t i = 0; st == MIXDIR_B200_OK && i < h->shards.size(); i++) {
+    Shard& s = h->shards[i];
+    st = init_shard_static(h, s);
+    if (st == MIXDIR_B200_OK)
+      st = upload_codes(h, s, (const uint8_t*)codes + (size_t)s.row0 * n_features * code_bytes);
+  }
+  if (st == MIXDIR_B200_OK) st = scan_codes(h);
+  if (st != MIXDIR_B200_OK) {
+    std::string keep = g_err;
+    mixdir_b200_destroy(h);
+    g_err = keep;
+    return st;
+  }
+  *out = h;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_create_from_r_matrix(const double* X, int64_t n_rows, int n_features,
+                                                const int* ncat, int n_devices,
+                                                const int* device_ids, mixdir_b200_handle** out) {
+  if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (n_rows < 0 || (n_rows > 0 && !X)) return fail(MIXDIR_B200_BAD_ARGUMENT, "X is NULL");
+  if (!ncat || n_features < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad ncat / n_features");
+  int cb = 1;
+  for (int j = 0; j < n_features; j++)
+    if (ncat[j] > 255) cb = 2;
+  mixdir_b200_handle* h = new mixdir_b200_handle();
+  int st = init_geometry(h, cb, n_features, ncat);
+  if (st == MIXDIR_B200_OK) st = make_shards(h, n_rows, n_devices, device_ids);
+  auto body = [&]() -> int {
+    for (auto& s : h->shards) {
+      RET_IF(init_shard_static(h, s));
+      // stream the fp64 column-major matrix through a staging buffer, pack on device
+      const int64_t chunk = std::min<int64_t>(std::max<int64_t>(s.n_rows, 1), 1 << 20);
+      double* d_x = nullptr;
+      int* d_bad = nullptr;
+      RET_IF(dalloc(&d_x, (size_t)chunk * n_features));
+      RET_IF(dalloc(&d_bad, 1));
+      CU_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), s.stream));
+      for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk) {
+        const int64_t nr = std::min(chunk, s.n_rows - r0);
+        CU_TRY(cudaMemcpy2DAsync(d_x, nr * sizeof(double), X + s.row0 + r0, n_rows * sizeof(double),
+                                 nr * sizeof(double), n_features, cudaMemcpyHostToDevice, s.stream));
+        uint8_t* dst = s.d_codes + (size_t)r0 * h->row_bytes;
+        const int grid = s.sm_count * 8;
+        if (cb == 1)
+          k_pack_r_matrix<1><<<grid, 256, 0, s.stream>>>(d_x, nr, nr, n_features, dst, h->row_bytes, d_bad);
+        else
+          k_pack_r_matrix<2><<<grid, 256, 0, s.stream>>>(d_x, nr, nr, n_features, dst, h->row_bytes, d_bad);
+        CU_TRY(cudaGetLastError());
+      }
+      int bad = 0;
+      CU_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      CU_TRY(cudaStreamSynchronize(s.stream));
+      cudaFree(d_x);
+      cudaFree(d_bad);
+      if (bad) return fail(MIXDIR_B200_BAD_ARGUMENT, "X holds a value that is not a positive integer code or NA");
+    }
+    return scan_codes(h);
+  };
+  if (st == MIXDIR_B200_OK) st = body();
+  if (st != MIXDIR_B200_OK) {
+    std::string keep = g_err;
+    mixdir_b200_destroy(h);
+    g_err = keep;
+    return st;
+  }
+  *out = h;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_nccl_unique_id(void* out128) {
+  if (!out128) return fail(MIXDIR_B200_BAD_ARGUMENT, "out128 is NULL");
+  RET_IF(nccl::load());
+  nccl::unique_id id;
+  NCCL_TRY(nccl::GetUniqueId(&id));
+  memcpy(out128, &id, sizeof id);
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_rows_local,
+                                       int n_features, const int* ncat, int device, int rank,
+                                       int world, const void* unique_id128,
+                                       mixdir_b200_handle** out) {
+  if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad rank/world");
+  if (world > 1 && !unique_id128) return fail(MIXDIR_B200_BAD_ARGUMENT, "unique_id128 is NULL");
+  if (n_rows_local < 0 || (n_rows_local > 0 && !codes_local))
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "codes_local is NULL");
+  mixdir_b200_handle* h = new mixdir_b200_handle();
+  h->rank = rank;
+  h->world = world;
+  int st = init_geometry(h, code_bytes, n_features, ncat);
+  auto body = [&]() -> int {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail(MIXDIR_B200_CUDA_ERROR, "no CUDA device available (mixdir_b200 has no CPU path)");
+    h->n_rows = n_rows_local;
+    h->shards.resize(1);
+    Shard& s = h->shards[0];
+    s.device = device;
+    s.row0 = 0;
+    s.n_rows = n_rows_local;
+    RET_IF(init_shard_static(h, s));
+    if (world > 1) {
+      RET_IF(nccl::load());
+      nccl::unique_id id;
+      memcpy(&id, unique_id128, sizeof id);
+      NCCL_TRY(nccl::CommInitRank(&s.comm, world, id, rank));
+    }
+    RET_IF(upload_codes(h, s, (const uint8_t*)codes_local));
+    return scan_codes(h);
+  };
+  if (st == MIXDIR_B200_OK) st = body();
+  if (st != MIXDIR_B200_OK) {
+    std::string keep = g_err;
+    mixdir_b200_destroy(h);
+    g_err = keep;
+    return st;
+  }
+  *out = h;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int64_t mixdir_b200_n_rows(const mixdir_b200_handle* h) { return h ? h->n_rows : -1; }
+extern "C" int mixdir_b200_max_code(const mixdir_b200_handle* h) { return h ? h->max_code : -1; }
+extern "C" int64_t mixdir_b200_n_missing(const mixdir_b200_handle* h) { return h ? h->n_missing : -1; }
+extern "C" const char* mixdir_b200_last_error(void) { return g_err.c_str(); }
+extern "C" int mixdir_b200_abi_version(void) { return MIXDIR_B200_ABI_VERSION; }
+extern "C" size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n_latent) {
+  size_t s = 0;
+  for (int j = 0; j < n_features; j++) s += (size_t)ncat[j];
+  return s * (size_t)n_latent;
+}
+extern "C" int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine) {
+  if (!h || engine < 0 || engine > 2) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  h->engine_pref = engine;
+  return MIXDIR_B200_OK;
+}
+extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out) {
+  if (!h || !out) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
+  *out = h->timing;
+  return MIXDIR_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// planning the fused kernel: classes per CTA (KC), cluster size (P), row groups
+// per warp (RG), warps (W) such that table + statistics slices fit shared memory
+// ---------------------------------------------------------------------------
+typedef void (*fused_fn)(FusedArgs);
+
+static fused_fn pick_fused(int KC, int CB, int RG) {
+#define PICK(kc, cb, rg) \
+  if (KC == kc && CB == cb && RG == rg) return k_em_fused<kc, cb, rg>;
+  PICK(32, 1, 8) PICK(32, 1, 4) PICK(32, 1, 2)
+  PICK(16, 1, 8) PICK(16, 1, 4) PICK(16, 1, 2)
+  PICK(8, 1, 8) PICK(8, 1, 4) PICK(8, 1, 2)
+  PICK(32, 2, 8) PICK(32, 2, 4) PICK(32, 2, 2)
+  PICK(16, 2, 8) PICK(16, 2, 4) PICK(16, 2, 2)
+#undef PICK
+  return nullptr;
+}
+
+static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+  Plan best;
+  double best_cost = 1e300;
+  if (h->engine_pref != 1) {
+    const int kcs[3] = {32, 16, 8};
+    for (int KC : kcs) {
+      const int RPW = 32 / KC, FPW = 4 / h->CB;
+      if (RPW > FPW) continue;
+      const int P = (K + KC - 1) / KC;
+      if (P > 8) continue;
+      const int RG = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
+      const int W = std::min(16, h->WPR);
+      FusedSmem L(h->NR, KC, W, RG, h->WPR, FPW, P);
+      if (L.total > (size_t)s.smem_optin) continue;
+      // cost ~ shared-memory wavefronts per row: P CTAs x (1 / rows-per-instruction) x conflict factor
+      const double conflict = KC == 8 ? 1.5 : 1.0;
+      const double cost = P * conflict / RPW + 1e-3 * P;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.engine = 2;
+        best.KC = KC;
+        best.P = P;
+        best.RG = RG;
+        best.W = W;
+        best.KP = P * KC;
+        best.smem = L.total;
+        best.R = W * RG * RPW;
+      }
+    }
+  }
+  if (best.engine == 2) {
+    fused_fn fn = pick_fused(best.KC, h->CB, best.RG);
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)best.smem);
+    int nclus = 0;
+    if (e == cudaSuccess) {
+      if (best.P > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(best.P * s.sm_count);
+        cfg.blockDim = dim3(32 * best.W);
+        cfg.dynamicSmemBytes = best.smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = best.P;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        e = cudaOccupancyMaxActiveClusters(&nclus, (const void*)fn, &cfg);
+      } else {
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)fn, 32 * best.W, best.smem);
+        nclus = nb * s.sm_count;
+      }
+    }
+    if (e != cudaSuccess || nclus < 1) {
+      cudaGetLastError();
+      if (h->engine_pref == 2)
+        return fail(MIXDIR_B200_CUDA_ERROR, std::string("fused kernel cannot be scheduled: ") +
+                                                cudaGetErrorString(e));
+      best = Plan();
+    } else {
+      best.n_clusters = nclus;
+    }
+  }
+  if (best.engine != 2) {
+    if (h->engine_pref == 2)
+      return fail(MIXDIR_B200_BAD_ARGUMENT, "fused kernel does not fit this problem shape (K, sum C_j)");
+    best = Plan();
+    best.engine = 1;
+    best.KP = (K + 7) & ~7;
+  }
+  *out = best;
+  return MIXDIR_B200_OK;
+}
+
+static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, int max_iter) {
+  CU_TRY(cudaSetDevice(s.device));
+  const int KP = pl.KP;
+  const int nclus = pl.engine == 2 ? pl.n_clusters : 0;
+  const int nctas = nclus * pl.P;
+  if (s.ws_K == K && s.ws_KP == KP && s.ws_iter >= max_iter && s.ws_clusters >= nclus &&
+      s.ws_ctas >= nctas)
+    return MIXDIR_B200_OK;
+  free_workspace(s);
+  const size_t tab = (size_t)h->NR * KP;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  RET_IF(dalloc(&s.d_T, tab));
+  RET_IF(dalloc(&s.d_phi, tab));
+  RET_IF(dalloc(&s.d_logU, tab));
+  RET_IF(dalloc(&s.d_stats, tab + KP + 2));
+  RET_IF(dalloc(&s.d_logprior, KP));
+  RET_IF(dalloc(&s.d_cs_a, kMaxClasses));
+  RET_IF(dalloc(&s.d_cs_b, kMaxClasses));
+  RET_IF(dalloc(&s.d_pieces, (size_t)h->J * K * 3));
+  RET_IF(dalloc(&s.d_trace, std::max(max_iter, 1)));
+  RET_IF(dalloc(&s.d_rag_a, rag));
+  RET_IF(dalloc(&s.d_rag_b, rag));
+  RET_IF(dalloc(&s.d_lambda, K));
+  RET_IF(dalloc(&s.d_lambda_pad, KP));
+  RET_IF(dalloc(&s.d_prior_out, 2 * K));
+  RET_IF(dalloc(&s.d_perm, K));
+  RET_IF(dalloc(&s.d_underflow, 1));
+  RET_IF(dalloc(&s.d_warn, 1));
+  RET_IF(dalloc(&s.d_prior, 1));
+  RET_IF(dalloc(&s.d_status, 1));
+  if (nclus > 0) {
+    RET_IF(dalloc(&s.d_Spart, (size_t)nclus * tab));
+    RET_IF(dalloc(&s.d_cspart, (size_t)nclus * KP));
+    RET_IF(dalloc(&s.d_Hpart, nctas));
+  }
+  CU_TRY(cudaMemsetAsync(s.d_T, 0, tab * sizeof(double), s.stream));
+  CU_TRY(cudaMemsetAsync(s.d_phi, 0, tab * sizeof(double), s.stream));
+  CU_TRY(cudaMemsetAsync(s.d_logU, 0, tab * sizeof(double), s.stream));
+  s.ws_K = K;
+  s.ws_KP = KP;
+  s.ws_iter = std::max(max_iter, 1);
+  s.ws_clusters = nclus;
+  s.ws_ctas = nctas;
+  return MIXDIR_B200_OK;
+}
+
+static int upload_ragoff(mixdir_b200_handle* h, Shard& s, int K) {
+  std::vector<int64_t> ro(h->J);
+  for (int j = 0; j < h->J; j++) ro[j] = h->ragoff1[j] * K;
+  CU_TRY(cudaMemcpyAsync(s.d_ragoff, ro.data(), h->J * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+  CU_TRY(cudaStreamSynchronize(s.stream));  // ro is a stack temporary
+  return MIXDIR_B200_OK;
+}
+
+// one E+M pass on a shard: statistics land in s.d_stats (local, before any all-reduce)
+static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, double* zeta_out,
+                     bool scatter, cudaEvent_t ev0, cudaEvent_t ev1, int* launches) {
+  CU_TRY(cudaSetDevice(s.device));
+  const size_t tab = (size_t)h->NR * pl.KP;
+  CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
+  if (pl.engine == 2 && s.n_rows > 0) {
+    const int n_tiles = (int)((s.n_rows + pl.R - 1) / pl.R);
+    const int nclus = std::min(pl.n_clusters, n_tiles);
+    FusedArgs a;
+    a.codes = reinterpret_cast<const uint32_t*>(s.d_codes);
+    a.n_rows = s.n_rows;
+    a.n_tiles = n_tiles;
+    a.WPR = h->WPR;
+    a.NR = h->NR;
+    a.K = K;
+    a.KP = pl.KP;
+    a.P = pl.P;
+    a.rowoff_pad = s.d_rowoff_pad;
+    a.T = s.d_T;
+    a.logprior = s.d_logprior;
+    a.Spart = s.d_Spart;
+    a.cspart = s.d_cspart;
+    a.Hpart = s.d_Hpart;
+    a.underflow = s.d_underflow;
+    fused_fn fn = pick_fused(pl.KC, h->CB, pl.RG);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nclus * pl.P);
+    cfg.blockDim = dim3(32 * pl.W);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = s.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.P;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, a));
+    if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
+    ReduceArgs r;
+    r.NR = h->NR;
+    r.KP = pl.KP;
+    r.n_clusters = nclus;
+    r.n_ctas = nclus * pl.P;
+    r.Spart = s.d_Spart;
+    r.cspart = s.d_cspart;
+    r.Hpart = s.d_Hpart;
+    r.underflow = s.d_underflow;
+    r.na_row = s.d_na_row;
+    r.stats = s.d_stats;
+    const int rgrid = (int)std::min<size_t>((tab + 255) / 256, (size_t)s.sm_count * 4);
+    k_reduce_partials<<<rgrid, 256, 0, s.stream>>>(r);
+    CU_TRY(cudaGetLastError());
+    *launches += 2;
+    h->timing.grid_ctas = nclus * pl.P;
+  } else {
+    CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 2) * sizeof(double), s.stream));
+    GenericArgs g;
+    g.codes = s.d_codes;
+    g.row_bytes = h->row_bytes;
+    g.n_rows = s.n_rows;
+    g.J = h->J;
+    g.K = K;
+    g.KP = pl.KP;
+    g.rowoff = s.d_rowoff;
+    g.T = s.d_T;
+    g.logprior = s.d_logprior;
+    g.stats = s.d_stats;
+    g.NR = h->NR;
+    g.underflow = s.d_underflow;
+    g.zeta_out = zeta_out;
+    g.do_scatter = scatter ? 1 : 0;
+    const int grid = s.sm_count * 8;
+    if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
+    if (s.n_rows > 0) {
+      if (h->CB == 1)
+        k_em_generic<1><<<grid, 256, 0, s.stream>>>(g);
+      else
+        k_em_generic<2><<<grid, 256, 0, s.stream>>>(g);
+      CU_TRY(cudaGetLastError());
+    }
+    if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
+    k_flag_to_stats<<<1, 1, 0, s.stream>>>(s.d_underflow, s.d_stats + tab + pl.KP + 1);
+    CU_TRY(cudaGetLastError());
+    *launches += 2;
+  }
+  return MIXDIR_B200_OK;
+}
+
+static int check_fit_args(const mixdir_b200_handle* h, const mixdir_b200_fit_params* p) {
+  if (!h || !p) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL handle or params");
+  if (p->n_latent < 1 || p->n_latent > kMaxClasses)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  if (p->max_iter < 0) return fail(MIXDIR_B200_BAD_ARGUMENT, "max_iter must be >= 0");
+  if (!(p->alpha1 > 0) || !(p->beta > 0) || (p->dp && !(p->alpha2 > 0)))
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "alpha and beta must be positive");
+  if (isnan(p->epsilon)) return fail(MIXDIR_B200_BAD_ARGUMENT, "epsilon is NaN");
+  return MIXDIR_B200_OK;
+}
+
+static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob, int32_t* pred_class);
+
+extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_params* p,
+                               const double* colsum_init, const double* phi_init,
+                               double* elbo_trace, int* n_iter, int* converged, double* elbo,
+                               double* lambda, double* prior_param, double* phi,
+                               double* category_prob, double* class_prob, int32_t* pred_class,
+                               int* warn_flags) {
+  RET_IF(check_fit_args(h, p));
+  if (!colsum_init || !phi_init) return fail(MIXDIR_B200_BAD_ARGUMENT, "colsum_init / phi_init is NULL");
+  const int K = p->n_latent, J = h->J;
+  const int n_cat_bound = p->n_cat_bound > 0 ? p->n_cat_bound : h->max_code;
+  Plan pl;
+  RET_IF(plan_engine(h, h->shards[0], K, &pl));
+  const size_t tab = (size_t)h->NR * pl.KP;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  const int jk_grid = (J * K + 127) / 128;
+  h->timing = mixdir_b200_timing();
+  h->timing.engine = pl.engine;
+  h->timing.classes_per_cta = pl.KC;
+  h->timing.cluster_size = pl.P;
+  h->timing.smem_bytes = (int)pl.smem;
+
+  // ---- initial state on every shard: class masses + table from phi_init ----
+  for (auto& s : h->shards) {
+    RET_IF(ensure_workspace(h, s, K, pl, p->max_iter));
+    RET_IF(upload_ragoff(h, s, K));
+    while ((int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
+      cudaEvent_t e;
+      CU_TRY(cudaEventCreate(&e));
+      s.ev_em.push_back(e);
+    }
+    CU_TRY(cudaMemcpyAsync(s.d_cs_a, colsum_init, K * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_rag_a, phi_init, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
+    CU_TRY(cudaMemsetAsync(s.d_warn, 0, sizeof(int), s.stream));
+    ScatterRagArgs ra = {J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_phi, 0, 0.0};
+    k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
+    ParamArgs pa = {J, K, pl.KP, p->dp, 0, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
+                    nullptr, nullptr, s.d_phi, s.d_T, nullptr, s.d_perm};
+    k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
+    CU_TRY(cudaGetLastError());
+  }
+
+  // ---- the coordinate-ascent loop (R/mixdir_vi.R:58-115) ----
+  int iters = 0, conv = 0, warn = 0, status = MIXDIR_B200_OK, launches = 0;
+  double last_elbo = NAN;
+  for (auto& s : h->shards) {
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaEventRecord(s.ev_loop0, s.stream));
+  }
+  std::vector<void*> stat_bufs(h->shards.size());
+  for (int it = 0; it < p->max_iter && !conv; it++) {
+    for (size_t si = 0; si < h->shards.size(); si++) {
+      Shard& s = h->shards[si];
+      CU_TRY(cudaSetDevice(s.device));
+      PriorArgs pr = {K, pl.KP, p->dp, p->alpha1, p->alpha2, s.d_cs_a, s.d_prior, s.d_logprior};
+      k_prior<<<1, 256, 0, s.stream>>>(pr);
+      CU_TRY(cudaGetLastError());
+      int l = 0;
+      RET_IF(launch_em(h, s, K, pl, nullptr, true, s.ev_em[2 * it], s.ev_em[2 * it + 1], &l));
+      if (si == 0) launches += 1 + l;
+      stat_bufs[si] = s.d_stats;
+    }
+    RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 2, nccl::kDouble, nccl::kSum));
+    for (size_t si = 0; si < h->shards.size(); si++) {
+      Shard& s = h->shards[si];
+      CU_TRY(cudaSetDevice(s.device));
+      ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
+                      s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
+      k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
+      FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, (double)K * (double)h->n_missing,
+                         s.d_pieces, s.d_stats + tab, s.d_stats + tab + pl.KP,
+                         s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior, s.d_cs_b, s.d_trace,
+                         s.d_status};
+      k_finalize<<<1, 256, 0, s.stream>>>(fa);
+      CU_TRY(cudaGetLastError());
+      std::swap(s.d_cs_a, s.d_cs_b);
+      if (si == 0) {
+        launches += 2;
+        CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(IterStatus), cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
+    {
+      Shard& s0 = h->shards[0];
+      CU_TRY(cudaSetDevice(s0.device));
+      CU_TRY(cudaStreamSynchronize(s0.stream));
+      iters = it + 1;
+      last_elbo = s0.h_status->elbo;
+      warn = s0.h_status->warn;
+      conv = s0.h_status->converged;
+      if (s0.h_status->underflow) {
+        status = MIXDIR_B200_UNDERFLOW;
+        break;
+      }
+    }
+  }
+  for (auto& s : h->shards) {
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaEventRecord(s.ev_loop1, s.stream));
+  }
+  for (auto& s : h->shards) {
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+  }
+  {
+    Shard& s0 = h->shards[0];
+    CU_TRY(cudaSetDevice(s0.device));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, s0.ev_loop0, s0.ev_loop1));
+    h->timing.fit_loop_ms = ms;
+    double em = 0;
+    for (int it = 0; it < iters; it++) {
+      CU_TRY(cudaEventElapsedTime(&ms, s0.ev_em[2 * it], s0.ev_em[2 * it + 1]));
+      em += ms;
+    }
+    h->timing.em_kernel_ms = em;
+    h->timing.iterations = iters;
+    h->timing.em_launches = iters;
+    h->timing.total_launches = launches;
+    if (elbo_trace && iters > 0)
+      CU_TRY(cudaMemcpy(elbo_trace, s0.d_trace, iters * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (n_iter) *n_iter = iters;
+  if (converged) *converged = conv;
+  if (elbo) *elbo = last_elbo;
+  if (status != MIXDIR_B200_OK) {
+    if (warn_flags) *warn_flags = warn;
+    return fail(status, "zeta underflow: some row has rowSums(zeta) == 0");
+  }
+
+  // ---- results (R/mixdir_vi.R:119-155) ----
+  for (size_t si = 0; si < h->shards.size(); si++) {
+    Shard& s = h->shards[si];
+    CU_TRY(cudaSetDevice(s.device));
+    ResultArgs ra = {J, K, pl.KP, p->dp, p->alpha1, p->alpha2, s.d_ncat, s.d_rowoff, s.d_ragoff,
+                     s.d_phi, s.d_cs_a, s.d_logU, s.d_rag_a, s.d_rag_b, s.d_lambda,
+                     s.d_lambda_pad, s.d_prior_out, s.d_warn};
+    k_results<<<jk_grid, 128, 0, s.stream>>>(ra);
+    CU_TRY(cudaGetLastError());
+    if (si == 0) {
+      int w2 = 0;
+      if (lambda) CU_TRY(cudaMemcpyAsync(lambda, s.d_lambda, K * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      if (prior_param)
+        CU_TRY(cudaMemcpyAsync(prior_param, s.d_prior_out, (p->dp ? 2 : 1) * K * sizeof(double),
+                               cudaMemcpyDeviceToHost, s.stream));
+      if (phi) CU_TRY(cudaMemcpyAsync(phi, s.d_rag_a, rag * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      if (category_prob)
+        CU_TRY(cudaMemcpyAsync(category_prob, s.d_rag_b, rag * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      CU_TRY(cudaMemcpyAsync(&w2, s.d_warn, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      CU_TRY(cudaStreamSynchronize(s.stream));
+      warn |= w2;
+    }
+  }
+  if (warn_flags) *warn_flags = warn;
+  if (class_prob || pred_class) RET_IF(run_predict(h, K, pl.KP, class_prob, pred_class));
+  return MIXDIR_B200_OK;
+}
+
+// final pass on every shard with the tables already in d_logU / d_lambda_pad
+static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob, int32_t* pred_class) {
+  for (auto& s : h->shards) {
+    if (s.n_rows == 0) continue;
+    CU_TRY(cudaSetDevice(s.device));
+    double* d_cp = nullptr;
+    int32_t* d_pc = nullptr;
+    if (class_prob) RET_IF(dalloc(&d_cp, (size_t)s.n_rows * K));
+    if (pred_class) RET_IF(dalloc(&d_pc, (size_t)s.n_rows));
+    PredictArgs a = {s.d_codes, h->row_bytes, s.n_rows, h->J, K, KP, s.d_rowoff, s.d_logU,
+                     s.d_lambda_pad, d_cp, d_pc};
+    const int grid = s.sm_count * 8;
+    if (h->CB == 1)
+      k_predict<1><<<grid, 256, 0, s.stream>>>(a);
+    else
+      k_predict<2><<<grid, 256, 0, s.stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    if (class_prob)  // shard block of an n_rows x K column-major matrix
+      CU_TRY(cudaMemcpy2DAsync(class_prob + s.row0, (size_t)h->n_rows * sizeof(double), d_cp,
+                               (size_t)s.n_rows * sizeof(double), (size_t)s.n_rows * sizeof(double),
+                               K, cudaMemcpyDeviceToHost, s.stream));
+    if (pred_class)
+      CU_TRY(cudaMemcpyAsync(pred_class + s.row0, d_pc, (size_t)s.n_rows * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    if (d_cp) cudaFree(d_cp);
+    if (d_pc) cudaFree(d_pc);
+  }
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const double* lambda,
+                                   const double* category_prob, double* class_prob,
+                                   int32_t* pred_class) {
+  if (!h || !lambda || !category_prob) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
+  const int K = n_latent;
+  if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  Plan pl;
+  pl.engine = 1;
+  pl.KP = (K + 7) & ~7;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  const int jk_grid = (h->J * K + 127) / 128;
+  std::vector<double> lpad(pl.KP, 0.0);
+  for (int k = 0; k < K; k++) lpad[k] = lambda[k];
+  for (auto& s : h->shards) {
+    RET_IF(ensure_workspace(h, s, K, pl, 1));
+    RET_IF(upload_ragoff(h, s, K));
+    CU_TRY(cudaMemcpyAsync(s.d_rag_a, category_prob, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_lambda_pad, lpad.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_logU, 1, 0.0};
+    k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s.stream));  // lpad is a local
+  }
+  return run_predict(h, K, pl.KP, class_prob, pred_class);
+}
+
+extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const double* log_prior,
+                                 const double* table, int engine, double* S, double* colsum,
+                                 double* entropy, int* underflow, double* zeta) {
+  if (!h || !log_prior || !table) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
+  const int K = n_latent;
+  if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  if (engine < 0 || engine > 2) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  const int keep = h->engine_pref;
+  if (engine) h->engine_pref = engine;
+  Plan pl;
+  int st = plan_engine(h, h->shards[0], K, &pl);
+  h->engine_pref = keep;
+  RET_IF(st);
+  const size_t tab = (size_t)h->NR * pl.KP;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  const int jk_grid = (h->J * K + 127) / 128;
+  std::vector<double> lp(pl.KP, -INFINITY);
+  for (int k = 0; k < K; k++) lp[k] = log_prior[k];
+  std::vector<void*> bufs(h->shards.size());
+  for (size_t si = 0; si < h->shards.size(); si++) {
+    Shard& s = h->shards[si];
+    RET_IF(ensure_workspace(h, s, K, pl, 1));
+    RET_IF(upload_ragoff(h, s, K));
+    CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_T, 0, 0.0};
+    k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    int l = 0;
+    double* d_zeta = nullptr;
+    if (zeta && s.n_rows > 0) {
+      RET_IF(dalloc(&d_zeta, (size_t)s.n_rows * K));
+      if (pl.engine == 2) {  // responsibilities come from the generic kernel (no scatter)
+        Plan g = pl;
+        g.engine = 1;
+        RET_IF(launch_em(h, s, K, g, d_zeta, false, nullptr, nullptr, &l));
+      }
+    }
+    RET_IF(launch_em(h, s, K, pl, pl.engine == 1 ? d_zeta : nullptr, true, nullptr, nullptr, &l));
+    if (d_zeta) {
+      CU_TRY(cudaMemcpy2DAsync(zeta + s.row0, (size_t)h->n_rows * sizeof(double), d_zeta,
+                               (size_t)s.n_rows * sizeof(double), (size_t)s.n_rows * sizeof(double),
+                               K, cudaMemcpyDeviceToHost, s.stream));
+      CU_TRY(cudaStreamSynchronize(s.stream));
+      cudaFree(d_zeta);
+    }
+    bufs[si] = s.d_stats;
+  }
+  RET_IF(allreduce(h, bufs, tab + pl.KP + 2, nccl::kDouble, nccl::kSum));
+  {
+    Shard& s = h->shards[0];
+    CU_TRY(cudaSetDevice(s.device));
+    ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, nullptr, s.d_stats, 0, 0.0};
+    k_table_to_ragged<<<jk_grid, 128, 0, s.stream>>>(ra, s.d_rag_b);
+    CU_TRY(cudaGetLastError());
+    std::vector<double> tail(pl.KP + 2);
+    if (S) CU_TRY(cudaMemcpyAsync(S, s.d_rag_b, rag * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaMemcpyAsync(tail.data(), s.d_stats + tab, (pl.KP + 2) * sizeof(double),
+                           cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    if (colsum) memcpy(colsum, tail.data(), K * sizeof(double));
+    if (entropy) *entropy = tail[pl.KP];
+    if (underflow) *underflow = tail[pl.KP + 1] > 0 ? 1 : 0;
+  }
+  h->timing.engine = pl.engine;
+  h->timing.classes_per_cta = pl.KC;
+  h->timing.cluster_size = pl.P;
+  h->timing.smem_bytes = (int)pl.smem;
+  return MIXDIR_B200_OK;
+}

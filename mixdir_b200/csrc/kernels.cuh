@@ -1,0 +1,1060 @@
+// mixdir_b200 device code (sm_100a).  Hand-written CUDA for the variational-
+// inference hot path of const-ae/mixdir:
+//   zeta E-step      /root/reference/src/mixdir_impl.cpp:57-87 (fixed K), :113-152 (DP)
+//   normalise+guard  /root/reference/R/mixdir_vi.R:77-82
+//   phi M-step       /root/reference/R/mixdir_vi.R:85-91
+//   ELBO             /root/reference/R/mixdir_vi.R:94-102,164-192; R/mixdir_vi_dp.R:110-118,196-221
+//   convergence      /root/reference/R/mixdir_vi.R:105-109
+//   final pass       /root/reference/R/mixdir_vi.R:119-148; R/predict.R:88-103
+//
+// Device data layout (DESIGN.md "Data layout in HBM"):
+//   codes   row-major, each row padded to a whole number of 32-bit words (WPR
+//           words); a cell is 1 or 2 bytes, 0 = NA.  The allocation carries 512
+//           extra all-zero rows so that a row tile may overrun n_rows.
+//   "category rows": feature j owns rows rowoff[j] .. rowoff[j]+C_j; row
+//           rowoff[j]+0 is the NA row (table value 0 => an NA cell adds nothing,
+//           mixdir_impl.cpp:79), row rowoff[j]+x belongs to category x.
+//           NR = sum_j (C_j + 1).
+//   tables  T[g][k], phi[g][k], S[g][k]: NR x KP doubles, class index fastest,
+//           KP >= K (padded classes carry log-prior -inf and never contribute).
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace mxd {
+
+namespace cg = cooperative_groups;
+
+// exp(x) == 0 in fp64 for x below ln(2^-1075); a row whose largest logit is
+// below this has rowSums(zeta) == 0 in the reference (R/mixdir_vi.R:77).
+__device__ constexpr double kExpUnderflow = -745.13321910194122211;
+constexpr int kMaxClasses = 256;  // K limit of the engine (8 classes per lane in the generic kernel)
+constexpr int kRowPad = 512;      // zero rows appended to the code matrix
+
+// digamma for x > 0: same recipe as the oracle (oracle/mixdir_oracle.c
+// oracle_digamma) so that host and device agree to a few ulp.
+__device__ __forceinline__ double dev_digamma(double x) {
+  if (!(x > 0.0)) return nan("");
+  double acc = 0.0;
+  while (x < 10.0) {
+    acc -= 1.0 / x;
+    x += 1.0;
+  }
+  const double inv = 1.0 / x;
+  const double inv2 = inv * inv;
+  double series = 1.0 / 12.0;
+  series = series * inv2 - 691.0 / 32760.0;
+  series = series * inv2 + 1.0 / 132.0;
+  series = series * inv2 - 1.0 / 240.0;
+  series = series * inv2 + 1.0 / 252.0;
+  series = series * inv2 - 1.0 / 120.0;
+  series = series * inv2 + 1.0 / 12.0;
+  return acc + (log(x) - 0.5 * inv - series * inv2);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// code scan at upload: NA count, largest code (the reference's n_cat,
+// R/mixdir_vi.R:8) and a validity check (code <= C_j).
+// ---------------------------------------------------------------------------
+struct ScanOut {
+  unsigned long long n_missing;
+  int max_code;
+  int bad;  // some code exceeded its feature's C_j
+};
+
+template <int CB>
+__global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, int64_t n_rows, int J,
+                             const int* __restrict__ ncat, ScanOut* out) {
+  unsigned long long miss = 0;
+  int mx = 0, bad = 0;
+  const int64_t total = n_rows * J;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = c / J;
+    const int j = (int)(c - i * J);
+    const uint8_t* rp = codes + i * row_bytes;
+    const int x = CB == 1 ? rp[j] : reinterpret_cast<const uint16_t*>(rp)[j];
+    miss += (x == 0);
+    mx = max(mx, x);
+    bad |= (x > ncat[j]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    miss += __shfl_xor_sync(0xffffffffu, miss, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out->n_missing, miss);
+    atomicMax(&out->max_code, mx);
+    if (bad) atomicOr(&out->bad, 1);
+  }
+}
+
+// fp64 column-major R matrix (NaN = NA) chunk -> packed row-major codes.
+// X chunk: rows [r0, r0+nr) of an n_total x J column-major matrix already on device.
+template <int CB>
+__global__ void k_pack_r_matrix(const double* __restrict__ X, int64_t ld, int64_t nr, int J,
+                                uint8_t* __restrict__ codes, int row_bytes, int* bad) {
+  const int64_t total = nr * J;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(c / nr);
+    const int64_t i = c - (int64_t)j * nr;  // consecutive threads -> consecutive rows (coalesced read)
+    const double v = X[i + (int64_t)j * ld];
+    int x = 0;
+    if (!isnan(v)) {
+      x = (int)v;
+      if (v < 1.0 || v != (double)x || x > (CB == 1 ? 255 : 65535)) {
+        *bad = 1;
+        x = 0;
+      }
+    }
+    if (CB == 1)
+      codes[i * row_bytes + j] = (uint8_t)x;
+    else
+      reinterpret_cast<uint16_t*>(codes + i * row_bytes)[j] = (uint16_t)x;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// prior step: omega / kappa from the class masses of the previous zeta, the
+// per-class prior logit, and the ELBO terms that depend on omega/kappa only.
+// One block.  K <= kMaxClasses.
+// ---------------------------------------------------------------------------
+struct PriorState {
+  double omega[kMaxClasses];   // omega (dp=0) or kappa1 (dp=1)
+  double kappa2[kMaxClasses];  // dp=1 only
+  double e1[kMaxClasses];      // psi(omega_k)-psi(sum omega)        | psi(k1)-psi(k1+k2)
+  double e2[kMaxClasses];      //                                     | psi(k2)-psi(k1+k2)
+  double termA;                // expec_log_lambda (R/mixdir_vi.R:164) | dp_expec_log_v (dp.R:196)
+  double termE;                // entrop_omega (R/mixdir_vi.R:177)     | dp_entrop_v (dp.R:214)
+};
+
+struct PriorArgs {
+  int K, KP, dp;
+  double a1, a2;
+  const double* cs;   // [K] class masses colSums(zeta) (R/mixdir_vi.R:61)
+  PriorState* st;
+  double* logprior;   // [KP] psi-part of the logit, WITHOUT the "-1" (mixdir_impl.cpp:83,148)
+};
+
+__global__ void k_prior(PriorArgs a) {
+  __shared__ double lg1[kMaxClasses], lg2[kMaxClasses], lg12[kMaxClasses], d1[kMaxClasses],
+      d2[kMaxClasses], d12[kMaxClasses];
+  const int K = a.K;
+  PriorState* st = a.st;
+  if (!a.dp) {
+    // omega <- alpha + colSums(zeta)   (R/mixdir_vi.R:61)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const double om = a.a1 + a.cs[k];
+      st->omega[k] = om;
+      d1[k] = dev_digamma(om);
+      lg1[k] = lgamma(om);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double so = 0;
+      for (int k = 0; k < K; k++) so += st->omega[k];
+      const double dso = dev_digamma(so);  // mixdir_impl.cpp:59
+      double sA = 0, sl = 0, sE = 0;
+      for (int k = 0; k < K; k++) {
+        const double e = d1[k] - dso;
+        st->e1[k] = e;
+        a.logprior[k] = e;
+        sA += (a.a1 - 1.0) * e;
+        sl += lg1[k];
+        sE += (st->omega[k] - 1.0) * e;
+      }
+      for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
+      st->termA = lgamma(K * a.a1) - K * lgamma(a.a1) + sA;  // R/mixdir_vi.R:164-166
+      st->termE = -lgamma(so) + sl - sE;                      // R/mixdir_vi.R:177-179
+    }
+  } else {
+    // kappa1 <- a1 + colSums(zeta); kappa2_k <- a2 + sum_{l>k} colSums(zeta)_l  (dp.R:68-71)
+    if (threadIdx.x == 0) {
+      double tail = 0;
+      for (int k = K - 1; k >= 0; k--) {
+        st->kappa2[k] = a.a2 + tail;
+        tail += a.cs[k];
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const double k1 = a.a1 + a.cs[k];
+      const double k2 = st->kappa2[k];
+      st->omega[k] = k1;
+      d1[k] = dev_digamma(k1);
+      d2[k] = dev_digamma(k2);
+      d12[k] = dev_digamma(k1 + k2);
+      lg1[k] = lgamma(k1);
+      lg2[k] = lgamma(k2);
+      lg12[k] = lgamma(k1 + k2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double skp = 0, sA = 0, sE = 0;
+      for (int k = 0; k < K; k++) {
+        const double k1 = st->omega[k], k2 = st->kappa2[k];
+        const double e1 = d1[k] - d12[k];
+        const double e2 = d2[k] - d12[k];
+        st->e1[k] = e1;
+        st->e2[k] = e2;
+        a.logprior[k] = e1 + skp;  // mixdir_impl.cpp:131-138,148
+        skp += e2;
+        sA += (a.a1 - 1.0) * e1 + (a.a2 - 1.0) * e2;  // dp.R:196-200
+        sE += lg1[k] + lg2[k] - lg12[k] - (k1 - 1.0) * d1[k] - (k2 - 1.0) * d2[k] +
+              (k1 + k2 - 2.0) * d12[k];  // dp.R:214-221
+      }
+      for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
+      st->termA = sA;
+      st->termE = sE;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// parameter step over (feature, class) pairs: [DP: re-order classes by mass]
+// -> phi = S + beta -> T = psi(phi) - psi(sum phi) -> per-(j,k) ELBO pieces.
+// ---------------------------------------------------------------------------
+struct ParamArgs {
+  int J, K, KP, dp;
+  int mode;           // 0: phi given (initial table); 1: phi from S (+ ELBO pieces)
+  int n_cat_bound;    // loop bound of the digamma-sum (mixdir_impl.cpp:65 quirk)
+  double beta;
+  const int* ncat;    // [J]
+  const int* rowoff;  // [J]
+  const double* S;    // [NR][KP]   (mode 1)
+  const double* cs;   // [KP] new class masses, unpermuted (mode 1)
+  double* phi;        // [NR][KP]
+  double* T;          // [NR][KP]
+  double* pieces;     // [J*K][3]: C-term, D-term, G-term per (j,k) (mode 1)
+  int* perm;          // [K] new class -> old class (written by block 0)
+};
+
+__global__ void k_param(ParamArgs a) {
+  __shared__ int perm[kMaxClasses];
+  const int K = a.K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (a.dp && a.mode == 1) {
+      // zeta <- zeta[, order(-colSums(zeta))]  (R/mixdir_vi_dp.R:97): stable, descending.
+      const double c = a.cs[k];
+      int rank = 0;
+      for (int l = 0; l < K; l++) {
+        const double cl = a.cs[l];
+        rank += (cl > c) || (cl == c && l < k);
+      }
+      perm[rank] = k;
+    } else {
+      perm[k] = k;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) a.perm[k] = perm[k];
+
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.J * K) return;
+  const int j = id / K, k = id - j * K;
+  const int C = a.ncat[j];
+  const size_t g0 = (size_t)a.rowoff[j];
+  const int old = perm[k];
+  const int KP = a.KP;
+
+  double sum_all = 0, sum_bound = 0;
+  for (int r = 0; r < C; r++) {
+    const size_t g = g0 + 1 + r;
+    // phi[[j]][[k]][r] <- sum(zeta[,k] * (X[,j]==r), na.rm=TRUE) + beta  (R/mixdir_vi.R:88)
+    const double ph = a.mode == 1 ? a.S[g * KP + old] + a.beta : a.phi[g * KP + k];
+    a.phi[g * KP + k] = ph;
+    sum_all += ph;
+    if (r < a.n_cat_bound) sum_bound += ph;
+  }
+  const double ds_bound = dev_digamma(sum_bound);  // mixdir_impl.cpp:61-72
+  const double ds_all = dev_digamma(sum_all);      // R-level digamma(sum(phi_jk))
+  double cpart = 0, dpart = 0, lgs = 0, gpart = 0;
+  for (int r = 0; r < C; r++) {
+    const size_t g = g0 + 1 + r;
+    const double ph = a.phi[g * KP + k];
+    const double dg = dev_digamma(ph);
+    const double t = dg - ds_bound;  // mixdir_impl.cpp:80
+    a.T[g * KP + k] = t;
+    if (a.mode == 1) {
+      cpart += (a.beta - 1.0) * (dg - ds_all);  // expec_log_ujk, R/mixdir_vi.R:172-174
+      dpart += a.S[g * KP + old] * t;           // expec_log_x_cpp collapsed
+      lgs += lgamma(ph);
+      gpart += (ph - 1.0) * (dg - ds_all);      // entrop_phi, R/mixdir_vi.R:190-192
+    }
+  }
+  a.T[g0 * KP + k] = 0.0;  // NA row
+  if (a.mode == 1) {
+    double* p = a.pieces + (size_t)id * 3;
+    p[0] = lgamma(C * a.beta) - C * lgamma(a.beta) + cpart;
+    p[1] = dpart;
+    p[2] = -lgamma(sum_all) + lgs - gpart;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// finalize: deterministic reduction of the (j,k) pieces, ELBO assembly
+// (R/mixdir_vi.R:94-102), convergence test (R/mixdir_vi.R:105-109), and the
+// class masses carried to the next iteration (permuted for DP).  One block.
+// ---------------------------------------------------------------------------
+struct IterStatus {
+  double elbo;
+  int converged;
+  int warn;
+  int underflow;
+  int iter;  // 0-based index of the iteration just finished
+};
+
+struct FinalizeArgs {
+  int J, K, KP, dp, iter;
+  double epsilon;
+  double k_times_nmissing;  // K * nNA: the "+1 per NA cell per class" of mixdir_impl.cpp:29-30
+  const double* pieces;     // [J*K][3]
+  const double* cs;         // [KP] new class masses (unpermuted)
+  const double* H;          // entropy sum (R/mixdir_vi.R:181-184)
+  const double* underflow;  // > 0 if any rank saw an underflowing row
+  const int* perm;          // [K]
+  const PriorState* st;
+  double* cs_next;          // [K] permuted class masses -> next k_prior
+  double* trace;            // [max_iter]
+  IterStatus* status;
+};
+
+__global__ void k_finalize(FinalizeArgs a) {
+  __shared__ double red[3][256];
+  const int n = a.J * a.K;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s0 += a.pieces[(size_t)i * 3 + 0];
+    s1 += a.pieces[(size_t)i * 3 + 1];
+    s2 += a.pieces[(size_t)i * 3 + 2];
+  }
+  red[0][threadIdx.x] = s0;
+  red[1][threadIdx.x] = s1;
+  red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+      red[2][threadIdx.x] += red[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const int K = a.K;
+  const double tC = red[0][0], tD = red[1][0] + a.k_times_nmissing, tG = red[2][0];
+  double tB = 0;
+  if (!a.dp) {
+    for (int k = 0; k < K; k++) {
+      const double c = a.cs[a.perm[k]];
+      a.cs_next[k] = c;
+      tB += c * a.st->e1[k];  // expec_log_zi summed over rows, R/mixdir_vi.R:168-170
+    }
+  } else {
+    double tail = 0;  // sum_{l>k} of the permuted class masses
+    for (int k = K - 1; k >= 0; k--) {
+      const double c = a.cs[a.perm[k]];
+      a.cs_next[k] = c;
+      tB += tail * a.st->e2[k] + c * a.st->e1[k];  // dp_expec_log_zi, dp.R:202-211
+      tail += c;
+    }
+  }
+  const double elbo = a.st->termA + tB + tC + tD + a.st->termE + (*a.H) + tG;
+  IterStatus* s = a.status;
+  int conv = 0, warn = s->warn;
+  if (a.iter != 0 && !isinf(elbo)) {
+    const double diff = elbo - a.trace[a.iter - 1];
+    if (diff < -a.epsilon) warn |= 1;  // R/mixdir_vi.R:105-108
+    if (diff < a.epsilon) conv = 1;    // R/mixdir_vi.R:109
+  }
+  a.trace[a.iter] = elbo;
+  s->elbo = elbo;
+  s->converged = conv;
+  s->warn = warn;
+  s->underflow = (*a.underflow > 0.0) ? 1 : 0;
+  s->iter = a.iter;
+}
+
+// ---------------------------------------------------------------------------
+// results: U = phi / sum(phi) (R/mixdir_vi.R:119-130), final omega/kappa and
+// lambda (R/mixdir_vi.R:132-133; R/mixdir_vi_dp.R:148-157), log-U table for the
+// final pass, and phi / U in the caller's ragged (j,k,r) layout.
+// ---------------------------------------------------------------------------
+struct ResultArgs {
+  int J, K, KP, dp;
+  double a1, a2;
+  const int* ncat;
+  const int* rowoff;
+  const int64_t* ragoff;  // [J] offset of feature j in the ragged layout (= K * sum_{j'<j} C_j')
+  const double* phi;      // [NR][KP]
+  const double* cs;       // [K] class masses of the final zeta (already permuted)
+  double* logU;           // [NR][KP] (NA row 0)
+  double* phi_rag;        // ragged out
+  double* U_rag;          // ragged out
+  double* lambda;         // [K]
+  double* loglambda_pad;  // [KP] lambda for the predict kernel (0 for padded classes)
+  double* prior_out;      // [K] or [2K]
+  int* warn;              // bit1 set if dp and lambda[K-1] > 0.01
+};
+
+__global__ void k_results(ResultArgs a) {
+  const int K = a.K, KP = a.KP;
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < a.J * K) {
+    const int j = id / K, k = id - j * K;
+    const int C = a.ncat[j];
+    const size_t g0 = (size_t)a.rowoff[j];
+    double s = 0;
+    for (int r = 0; r < C; r++) s += a.phi[(g0 + 1 + r) * KP + k];
+    for (int r = 0; r < C; r++) {
+      const double ph = a.phi[(g0 + 1 + r) * KP + k];
+      const double u = ph / s;
+      a.logU[(g0 + 1 + r) * KP + k] = log(u);
+      a.phi_rag[a.ragoff[j] + (int64_t)k * C + r] = ph;
+      a.U_rag[a.ragoff[j] + (int64_t)k * C + r] = u;
+    }
+    a.logU[g0 * KP + k] = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!a.dp) {
+      double so = 0;
+      for (int k = 0; k < K; k++) so += a.a1 + a.cs[k];
+      for (int k = 0; k < K; k++) {
+        const double om = a.a1 + a.cs[k];
+        a.prior_out[k] = om;
+        a.lambda[k] = om / so;
+      }
+    } else {
+      double tail = 0;
+      for (int k = K - 1; k >= 0; k--) {
+        a.prior_out[K + k] = a.a2 + tail;
+        tail += a.cs[k];
+      }
+      double prod = 1.0;
+      for (int k = 0; k < K; k++) {
+        const double k1 = a.a1 + a.cs[k];
+        a.prior_out[k] = k1;
+        const double nu = k1 / (k1 + a.prior_out[K + k]);
+        a.lambda[k] = nu * prod;
+        prod *= (1.0 - nu);
+      }
+      if (a.lambda[K - 1] > 0.01) atomicOr(a.warn, 2);
+    }
+    for (int k = 0; k < KP; k++) a.loglambda_pad[k] = k < K ? a.lambda[k] : 0.0;
+  }
+}
+
+// caller-supplied ragged table -> device table layout (NA row = fill)
+struct ScatterRagArgs {
+  int J, K, KP;
+  const int* ncat;
+  const int* rowoff;
+  const int64_t* ragoff;
+  const double* rag;
+  double* tab;
+  int take_log;  // 1: tab = log(rag)
+  double na_fill;
+};
+__global__ void k_ragged_to_table(ScatterRagArgs a) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.J * a.K) return;
+  const int j = id / a.K, k = id - j * a.K;
+  const int C = a.ncat[j];
+  const size_t g0 = (size_t)a.rowoff[j];
+  for (int r = 0; r < C; r++) {
+    const double v = a.rag[a.ragoff[j] + (int64_t)k * C + r];
+    a.tab[(g0 + 1 + r) * a.KP + k] = a.take_log ? log(v) : v;
+  }
+  a.tab[g0 * a.KP + k] = a.na_fill;
+}
+// device table layout -> ragged (j,k,r)
+__global__ void k_table_to_ragged(ScatterRagArgs a, double* out) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.J * a.K) return;
+  const int j = id / a.K, k = id - j * a.K;
+  const int C = a.ncat[j];
+  const size_t g0 = (size_t)a.rowoff[j];
+  for (int r = 0; r < C; r++) out[a.ragoff[j] + (int64_t)k * C + r] = a.tab[(g0 + 1 + r) * a.KP + k];
+}
+
+// ---------------------------------------------------------------------------
+// statistics buffer:  [ S : NR*KP | cs : KP | H | underflow ]   (doubles)
+// ---------------------------------------------------------------------------
+
+// deterministic reduction of the per-cluster partials of the fused kernel
+struct ReduceArgs {
+  int NR, KP;
+  int n_clusters, n_ctas;
+  const double* Spart;   // [n_clusters][NR*KP]
+  const double* cspart;  // [n_clusters][KP]
+  const double* Hpart;   // [n_ctas]
+  const int* underflow;  // device flag
+  const uint8_t* na_row; // [NR] 1 for NA rows (their S entries are scratch)
+  double* stats;
+};
+__global__ void k_reduce_partials(ReduceArgs a) {
+  const size_t n = (size_t)a.NR * a.KP;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x) {
+    double s = 0;
+    if (!a.na_row[e / a.KP])
+      for (int c = 0; c < a.n_clusters; c++) s += a.Spart[(size_t)c * n + e];
+    a.stats[e] = s;
+  }
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < a.KP; k += blockDim.x) {
+      double s = 0;
+      for (int c = 0; c < a.n_clusters; c++) s += a.cspart[(size_t)c * a.KP + k];
+      a.stats[n + k] = s;
+    }
+    if (threadIdx.x == 0) {
+      double h = 0;
+      for (int c = 0; c < a.n_ctas; c++) h += a.Hpart[c];
+      a.stats[n + a.KP] = h;
+      a.stats[n + a.KP + 1] = (*a.underflow) ? 1.0 : 0.0;
+    }
+  }
+}
+
+__global__ void k_flag_to_stats(const int* underflow, double* slot) {
+  *slot = (*underflow) ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// generic E+M pass: any K <= 256, any table size; tables stay in global/L2,
+// statistics accumulate with fp64 global atomics.  Correct everywhere; used
+// when the fused kernel's shared-memory plan does not fit, for the zeta-output
+// unit-test door, and as an on-device cross-check of the fused kernel.
+// ---------------------------------------------------------------------------
+struct GenericArgs {
+  const uint8_t* codes;
+  int row_bytes;
+  int64_t n_rows;
+  int J, K, KP;
+  const int* rowoff;
+  const double* T;         // [NR][KP]
+  const double* logprior;  // [KP]
+  double* stats;           // S | cs | H | (flag slot unused here); nullable S when only zeta wanted
+  int NR;
+  int* underflow;
+  double* zeta_out;        // nullable; n_rows x K column-major
+  int do_scatter;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(256) k_em_generic(GenericArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int K = a.K, KP = a.KP;
+  const int cpl = (K + 31) >> 5;
+  double csacc[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) csacc[c] = 0;
+  double hacc = 0;
+  const double kTiny = DBL_MIN * log(DBL_MIN);
+
+  for (int64_t row = gw; row < a.n_rows; row += nw) {
+    const uint8_t* rp = a.codes + row * a.row_bytes;
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = 0;
+    for (int j = 0; j < a.J; j++) {
+      const int x = CB == 1 ? rp[j] : reinterpret_cast<const uint16_t*>(rp)[j];
+      if (x) {
+        const double* t = a.T + (size_t)(a.rowoff[j] + x) * KP;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int k = lane + 32 * c;
+          if (c < cpl && k < K) acc[c] += __ldg(t + k);
+        }
+      }
+    }
+    double l[8], m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int k = lane + 32 * c;
+      l[c] = (c < cpl && k < K) ? (a.logprior[k] + acc[c]) - 1.0 : -INFINITY;  // impl.cpp:83
+      m = fmax(m, l[c]);
+    }
+    m = warp_max(m);
+    if (m < kExpUnderflow) {  // rowSums(zeta) == 0  (R/mixdir_vi.R:77)
+      if (lane == 0) atomicExch(a.underflow, 1);
+      continue;
+    }
+    double e[8], s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      e[c] = (l[c] == -INFINITY) ? 0.0 : exp(l[c] - m);
+      s += e[c];
+    }
+    s = warp_sum(s);
+    const double logs = log(s);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int k = lane + 32 * c;
+      if (c < cpl && k < K) {
+        const double z = e[c] / s;  // zeta / rowSums(zeta)  (R/mixdir_vi.R:82)
+        e[c] = z;
+        csacc[c] += z;
+        hacc -= (z > DBL_MIN) ? z * ((l[c] - m) - logs) : kTiny;  // entrop_zeta, R/mixdir_vi.R:181
+        if (a.zeta_out) a.zeta_out[row + (int64_t)k * a.n_rows] = z;
+      }
+    }
+    if (a.do_scatter) {
+      for (int j = 0; j < a.J; j++) {
+        const int x = CB == 1 ? rp[j] : reinterpret_cast<const uint16_t*>(rp)[j];
+        if (x) {
+          double* sp = a.stats + (size_t)(a.rowoff[j] + x) * KP;
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const int k = lane + 32 * c;
+            if (c < cpl && k < K) atomicAdd(sp + k, e[c]);
+          }
+        }
+      }
+    }
+  }
+  if (a.do_scatter) {
+    double* csg = a.stats + (size_t)a.NR * KP;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int k = lane + 32 * c;
+      if (c < cpl && k < K) atomicAdd(csg + k, csacc[c]);
+    }
+    hacc = warp_sum(hacc);
+    if (lane == 0) atomicAdd(csg + KP, hacc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// final pass / predict:  prob_z[i,k] = lambda_k * exp(sum_j log U[j,k,x_ij]),
+// row-normalised without max shift (R/mixdir_vi.R:136-141, R/predict.R:88-103),
+// pred_class = which.max (first maximum).
+// ---------------------------------------------------------------------------
+struct PredictArgs {
+  const uint8_t* codes;
+  int row_bytes;
+  int64_t n_rows;
+  int J, K, KP;
+  const int* rowoff;
+  const double* logU;    // [NR][KP], NA row 0
+  const double* lambda;  // [KP]
+  double* class_prob;    // nullable; n_rows x K column-major
+  int32_t* pred_class;   // nullable
+};
+
+template <int CB>
+__global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int K = a.K, KP = a.KP;
+  const int cpl = (K + 31) >> 5;
+  for (int64_t row = gw; row < a.n_rows; row += nw) {
+    const uint8_t* rp = a.codes + row * a.row_bytes;
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = 0;
+    for (int j = 0; j < a.J; j++) {
+      const int x = CB == 1 ? rp[j] : reinterpret_cast<const uint16_t*>(rp)[j];
+      if (x) {
+        const double* t = a.logU + (size_t)(a.rowoff[j] + x) * KP;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int k = lane + 32 * c;
+          if (c < cpl && k < K) acc[c] += __ldg(t + k);
+        }
+      }
+    }
+    double p[8], s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int k = lane + 32 * c;
+      p[c] = (c < cpl && k < K) ? a.lambda[k] * exp(acc[c]) : 0.0;
+      s += p[c];
+    }
+    s = warp_sum(s);
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int k = lane + 32 * c;
+      if (c < cpl && k < K) {
+        const double q = p[c] / s;
+        if (a.class_prob) a.class_prob[row + (int64_t)k * a.n_rows] = q;
+        if (q > bv || (q == bv && k < bi)) {
+          bv = q;
+          bi = k;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (a.pred_class && lane == 0) a.pred_class[row] = (bi == 0x7fffffff) ? 0 : bi + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FUSED E+M pass (the hot kernel).  See DESIGN.md "Fused kernel".
+//
+//  * persistent thread-block clusters of P CTAs; CTA `rank` owns the KC classes
+//    [rank*KC, rank*KC+KC): its slice of the table T and of the statistics S
+//    lives in shared memory for the whole launch (no atomics anywhere).
+//  * lanes = classes: a warp instruction covers RPW = 32/KC rows ("slots").
+//  * row tiles arrive through the TMA engine (cp.async.bulk + mbarrier),
+//    double buffered; every CTA of the cluster pulls the same tile (the second
+//    read is an L2 hit).
+//  * E-step: per row, J table gathers from shared memory, added in feature
+//    order exactly like mixdir_impl.cpp:77-82; soft-max over the classes with
+//    warp shuffles inside the CTA and one (max, sum) exchange over distributed
+//    shared memory across the cluster.
+//  * M-step: warps own rows; the features are cut into G word-groups and warp w
+//    works on group (w + t) mod G at step t, with a block barrier between
+//    steps, so no two warps ever touch the same histogram rows; the slots of a
+//    warp rotate the byte order so they never share a feature either.  Plain
+//    shared-memory read-modify-write, fp64.
+//  * flush: per-cluster partials to global, reduced in fixed order by
+//    k_reduce_partials (bit-reproducible run to run).
+// ---------------------------------------------------------------------------
+struct FusedArgs {
+  const uint32_t* codes;  // [n_rows + kRowPad][WPR]
+  int64_t n_rows;
+  int n_tiles;
+  int WPR;
+  int NR;
+  int K, KP;
+  int P;                  // cluster size
+  const int* rowoff_pad;  // [WPR*FPW]: category-row offset per (padded) feature
+  const double* T;
+  const double* logprior;
+  double* Spart;
+  double* cspart;
+  double* Hpart;
+  int* underflow;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int FPW>
+__device__ __forceinline__ void load_ro(const int* ro_s, int w, int* ro) {
+  if constexpr (FPW == 4) {
+    const int4 r = reinterpret_cast<const int4*>(ro_s)[w];
+    ro[0] = r.x; ro[1] = r.y; ro[2] = r.z; ro[3] = r.w;
+  } else {
+    const int2 r = reinterpret_cast<const int2*>(ro_s)[w];
+    ro[0] = r.x; ro[1] = r.y;
+  }
+}
+
+template <int KC, int CB, int RG>
+struct FusedCfg {
+  static constexpr int RPW = 32 / KC;  // rows per warp instruction
+  static constexpr int FPW = 4 / CB;   // features per 32-bit code word
+  static_assert(RPW <= FPW, "slots of a warp must be able to take distinct features of a word");
+};
+
+// dynamic shared memory carve-up, shared by host (sizing) and device
+struct FusedSmem {
+  size_t off_T, off_S, off_tile, off_exch, off_ro, off_red, off_bar, total;
+  __host__ __device__ FusedSmem(int NR, int KC, int W, int RG, int WPR, int FPW, int P) {
+    const int RPW = 32 / KC;
+    const size_t R = (size_t)W * RG * RPW;
+    size_t o = 0;
+    off_T = o;     o += (size_t)NR * KC * 8;
+    off_S = o;     o += (size_t)NR * KC * 8;
+    off_tile = o;  o += 2 * R * WPR * 4;
+    o = (o + 15) & ~(size_t)15;
+    off_exch = o;  o += (P > 1) ? 2 * R * P * 16 : 0;
+    off_ro = o;    o += (size_t)WPR * FPW * 4;
+    o = (o + 15) & ~(size_t)15;
+    off_red = o;   o += (size_t)(W * KC + W) * 8;
+    off_bar = o;   o += 16;
+    total = o;
+  }
+};
+
+template <int KC, int CB, int RG>
+__global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
+  using Cfg = FusedCfg<KC, CB, RG>;
+  constexpr int RPW = Cfg::RPW, FPW = Cfg::FPW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int P = a.P;
+  const int rank = (P > 1) ? (int)cluster.block_rank() : 0;
+  const int cluster_id = blockIdx.x / P;
+  const int n_clusters = gridDim.x / P;
+  const int W = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = lane / KC, kc = lane % KC;
+  const int kg = rank * KC + kc;  // global (padded) class index of this lane
+  const int WPR = a.WPR, NR = a.NR, KP = a.KP;
+  const int R = W * RG * RPW;  // rows per tile
+
+  const FusedSmem L(NR, KC, W, RG, WPR, FPW, P);
+  double* T_s = reinterpret_cast<double*>(smem_raw + L.off_T);
+  double* S_s = reinterpret_cast<double*>(smem_raw + L.off_S);
+  uint32_t* tile_s = reinterpret_cast<uint32_t*>(smem_raw + L.off_tile);
+  double2* exch_s = reinterpret_cast<double2*>(smem_raw + L.off_exch);
+  int* ro_s = reinterpret_cast<int*>(smem_raw + L.off_ro);
+  double* red_s = reinterpret_cast<double*>(smem_raw + L.off_red);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+
+  const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
+
+  // ---- prologue: barriers, first tile in flight, tables into shared memory ----
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && cluster_id < a.n_tiles) {
+    mbar_expect_tx(&bar[0], tile_bytes);
+    tma_load_1d(tile_s, a.codes + (size_t)cluster_id * R * WPR, tile_bytes, &bar[0]);
+  }
+  for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
+    const int g = i / KC, c = i - g * KC;
+    T_s[i] = a.T[(size_t)g * KP + rank * KC + c];
+    S_s[i] = 0.0;
+  }
+  for (int i = threadIdx.x; i < WPR * FPW; i += blockDim.x) ro_s[i] = a.rowoff_pad[i] * KC;
+  const double lp = a.logprior[kg];
+  const bool kreal = kg < a.K;
+  __syncthreads();
+  if (P > 1) cluster.sync();  // every CTA of the cluster is resident before DSMEM traffic
+
+  const double* Tl = T_s + kc;
+  double* Sl = S_s + kc;
+  double csacc = 0, hacc = 0;
+  int uflag = 0;
+  const double kTiny = DBL_MIN * log(DBL_MIN);
+  const int row_in_tile0 = warp * RG * RPW + slot;  // + rg*RPW
+
+  int it = 0;
+  for (int t = cluster_id; t < a.n_tiles; t += n_clusters, ++it) {
+    const int buf = it & 1;
+    const uint32_t* tile = tile_s + (size_t)buf * R * WPR;
+    // prefetch the next tile of this cluster into the other buffer (its last
+    // readers finished at the closing barrier of the previous iteration)
+    if (threadIdx.x == 0 && t + n_clusters < a.n_tiles) {
+      mbar_expect_tx(&bar[buf ^ 1], tile_bytes);
+      tma_load_1d(tile_s + (size_t)(buf ^ 1) * R * WPR,
+                  a.codes + (size_t)(t + n_clusters) * R * WPR, tile_bytes, &bar[buf ^ 1]);
+    }
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+
+    // ---- E-step gather: acc[rg] = sum_j T[j, x_ij, k] in feature order ----
+    double acc[RG];
+#pragma unroll
+    for (int rg = 0; rg < RG; rg++) acc[rg] = 0.0;
+    const uint32_t* trow = tile + (size_t)row_in_tile0 * WPR;
+    for (int w = 0; w < WPR; w++) {
+      int ro[FPW];
+      load_ro<FPW>(ro_s, w, ro);
+#pragma unroll
+      for (int rg = 0; rg < RG; rg++) {
+        const uint32_t cw = trow[(size_t)rg * RPW * WPR + w];
+#pragma unroll
+        for (int f = 0; f < FPW; f++) {
+          const uint32_t x = CB == 1 ? ((cw >> (8 * f)) & 0xffu) : ((cw >> (16 * f)) & 0xffffu);
+          acc[rg] += Tl[ro[f] + (int)x * KC];
+        }
+      }
+    }
+
+    // ---- soft-max over classes (R/mixdir_vi.R:82), cluster-wide ----
+    double lg[RG], z[RG], mloc[RG];
+#pragma unroll
+    for (int rg = 0; rg < RG; rg++) {
+      const double l = (lp + acc[rg]) - 1.0;  // mixdir_impl.cpp:83 / :148
+      double m = l;
+#pragma unroll
+      for (int o = KC / 2; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const double e = (l == -INFINITY) ? 0.0 : exp(l - m);
+      double s = e;
+#pragma unroll
+      for (int o = KC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      lg[rg] = l;
+      mloc[rg] = m;
+      z[rg] = e;
+      acc[rg] = s;  // reuse: local sum
+    }
+    if (P > 1) {
+      double2* ex = exch_s + (size_t)buf * R * P;
+#pragma unroll
+      for (int rg = 0; rg < RG; rg++) {
+        if (kc < P) {
+          double2* dst = cluster.map_shared_rank(&ex[(size_t)(row_in_tile0 + rg * RPW) * P + rank], kc);
+          *dst = make_double2(mloc[rg], acc[rg]);
+        }
+      }
+      cluster.sync();
+#pragma unroll
+      for (int rg = 0; rg < RG; rg++) {
+        double mp = -INFINITY, sp = 0.0;
+        if (kc < P) {
+          const double2 v = ex[(size_t)(row_in_tile0 + rg * RPW) * P + kc];
+          mp = v.x;
+          sp = v.y;
+        }
+        double M = mp;
+#pragma unroll
+        for (int o = KC / 2; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+        double term = (kc < P && mp != -INFINITY) ? sp * exp(mp - M) : 0.0;
+#pragma unroll
+        for (int o = KC / 2; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+        // rescale the local exponentials to the cluster-wide maximum
+        z[rg] = (mloc[rg] == -INFINITY) ? 0.0 : z[rg] * exp(mloc[rg] - M);
+        mloc[rg] = M;
+        acc[rg] = term;
+      }
+    }
+#pragma unroll
+    for (int rg = 0; rg < RG; rg++) {
+      const int64_t grow = (int64_t)t * R + row_in_tile0 + rg * RPW;
+      const bool valid = grow < a.n_rows;
+      const double M = mloc[rg], stot = acc[rg];
+      double zz = 0.0;
+      if (valid) {
+        if (M < kExpUnderflow) uflag = 1;  // rowSums(zeta) == 0  (R/mixdir_vi.R:77)
+        if (kreal) {
+          zz = z[rg] / stot;
+          hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - log(stot)) : kTiny;  // R/mixdir_vi.R:181
+          csacc += zz;
+        }
+      }
+      z[rg] = zz;
+    }
+
+    // ---- M-step scatter: rotating feature-group schedule, no atomics ----
+    // Warp w works on code word (w + step) mod WPR, so no two warps share a
+    // feature between two block barriers.  Inside a warp the RPW slots (rows)
+    // start SB features apart in the word and advance in batches of SB features,
+    // so in every batch the slots touch disjoint features; the SB read-modify-
+    // writes of a batch are independent and overlap.
+    constexpr int SB = FPW / RPW;
+    for (int step = 0; step < WPR; step++) {
+      int g = warp + step;
+      if (g >= WPR) g -= WPR;
+      int ro0[FPW], ro[FPW];
+      load_ro<FPW>(ro_s, g, ro0);
+#pragma unroll
+      for (int f = 0; f < FPW; f++) {
+        ro[f] = ro0[f];
+#pragma unroll
+        for (int sl = 1; sl < RPW; sl++)
+          if (slot == sl) ro[f] = ro0[(f + SB * sl) % FPW];
+      }
+#pragma unroll
+      for (int rg = 0; rg < RG; rg++) {
+        uint32_t cw = trow[(size_t)rg * RPW * WPR + g];
+        cw = __funnelshift_r(cw, cw, (8 * CB * SB * slot) & 31);
+#pragma unroll
+        for (int b = 0; b < RPW; b++) {
+          int idx[SB];
+          double v[SB];
+#pragma unroll
+          for (int f = 0; f < SB; f++) {
+            const int ff = b * SB + f;
+            const uint32_t x = CB == 1 ? ((cw >> (8 * ff)) & 0xffu) : ((cw >> (16 * ff)) & 0xffffu);
+            idx[f] = ro[ff] + (int)x * KC;
+            v[f] = Sl[idx[f]];
+          }
+#pragma unroll
+          for (int f = 0; f < SB; f++) Sl[idx[f]] = v[f] + z[rg];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- flush: this CTA's class slice of S, class masses, entropy ----
+  {
+    double* Sp = a.Spart + (size_t)cluster_id * NR * KP;
+    for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
+      const int g = i / KC, c = i - g * KC;
+      Sp[(size_t)g * KP + rank * KC + c] = S_s[i];
+    }
+#pragma unroll
+    for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);
+    hacc = warp_sum(hacc);
+    if (slot == 0) red_s[warp * KC + kc] = csacc;
+    if (lane == 0) red_s[W * KC + warp] = hacc;
+    __syncthreads();
+    if (threadIdx.x < KC) {
+      double s = 0;
+      for (int w = 0; w < W; w++) s += red_s[w * KC + threadIdx.x];
+      a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) {
+      double h = 0;
+      for (int w = 0; w < W; w++) h += red_s[W * KC + w];
+      a.Hpart[blockIdx.x] = h;
+    }
+    if (uflag) atomicExch(a.underflow, 1);
+  }
+  if (P > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+}
+
+}  // namespace mxd

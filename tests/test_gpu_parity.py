@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ctypes), against the CPU oracle
+and the committed golden fixtures.  Tolerances are north_star's: pred_class identical,
+class_prob within 1e-6 absolute, ELBO within 1e-9 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, subset_recode
+from mixdir_b200 import Engine, ZetaUnderflow, MixdirError, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+CP_ATOL = 1e-6    # class_prob, absolute   (north_star)
+ELBO_RTOL = 1e-9  # ELBO, relative         (north_star)
+
+FIT_FIXTURES = [
+    "fit_toy_k3.npz", "fit_toy_dp_k10.npz", "fit_toy_na_k3.npz", "fit_toy_na_dp_k10.npz",
+    "fit_m1_seed1.npz", "fit_m1_seed2.npz", "fit_m1_seed3.npz", "fit_m1_seed4.npz",
+    "fit_m2_dp_k10.npz", "fit_m2_dp_k20.npz", "fit_m2_k5.npz",
+    "fit_s3_small.npz", "fit_s3_small_dp.npz", "fit_s4_small.npz", "fit_unused_level.npz",
+]
+
+
+def fixture_codes(name, g, mushroom):
+    if "codes" in g:
+        return g["codes"]
+    if name.startswith("fit_m1"):
+        return subset_recode(mushroom["codes"], mushroom["categories"], range(1000), range(5))[0]
+    return mushroom["codes"]
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300))
+
+
+@pytest.mark.parametrize("engine", [1, 2], ids=["generic", "fused"])
+@pytest.mark.parametrize("name", FIT_FIXTURES)
+def test_fit_matches_golden(name, engine, mushroom):
+    g = load_golden(name)
+    codes = fixture_codes(name, g, mushroom)
+    ncat, K, dp, seed = g["ncat"], int(g["K"]), int(g["dp"]), int(g["seed"])
+    N = codes.shape[0]
+    z0 = synth.zeta_init(seed, N, K)
+    p0 = synth.phi_init(seed, ncat, K)
+    with Engine(codes, ncat) as eng:
+        eng.set_engine(engine)
+        try:
+            r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), alpha=g["alpha"], beta=float(g["beta"]),
+                        max_iter=int(g["max_iter"]), epsilon=float(g["epsilon"]))
+        except MixdirError as e:
+            if engine == 2 and "does not fit" in str(e):
+                pytest.skip("fused plan does not fit this shape")
+            raise
+        t = eng.timing()
+    assert t["engine"] == engine
+    ref_trace = g["convergence"]
+    assert r["n_iter"] == len(ref_trace), (r["n_iter"], len(ref_trace))
+    assert rel(r["convergence"], ref_trace) < ELBO_RTOL
+    assert r["converged"] == bool(g["converged"])
+    assert abs(r["ELBO"] - float(g["ELBO"])) <= ELBO_RTOL * abs(float(g["ELBO"]))
+    np.testing.assert_allclose(r["lambda_"], g["lambda_"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(r["phi"], g["phi"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r["category_prob"], g["category_prob"], rtol=1e-8, atol=1e-10)
+    prior = np.concatenate([r["kappa1"], r["kappa2"]]) if dp else r["omega"]
+    np.testing.assert_allclose(prior, g["prior"], rtol=1e-9, atol=1e-9)
+    assert np.max(np.abs(r["class_prob"][g["rows"]] - g["class_prob_rows"])) < CP_ATOL
+    assert np.array_equal(r["pred_class"], g["pred_class"])  # identical class assignments
+    assert r["warn_flags"] == int(g["warn_flags"])
+
+
+@pytest.mark.parametrize("engine", [1, 2], ids=["generic", "fused"])
+@pytest.mark.parametrize("tag", ["k3", "k10"])
+def test_estep_matches_reference_native_functions(tag, engine):
+    """kernel zeta / statistics vs the reference's own update_zeta_cpp / update_zeta_dp_cpp /
+    expec_log_x_cpp outputs (tests/golden/native_vectors.npz, produced by oracle/_ref);
+    mirrors tests/testthat/test_cpp.R:15-122."""
+    g = load_golden("native_vectors.npz")
+    codes, ncat = g["codes"], g["ncat"]
+    K = 3 if tag == "k3" else 10
+    phi, omega, kappa2 = g[f"phi_{tag}"], g[f"omega_{tag}"], g[f"kappa2_{tag}"]
+    n_cat = int(codes.max())
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import fused_model as fm
+    T = fm.table_from_phi(phi, ncat, K, n_cat)
+    with Engine(codes, ncat) as eng:
+        for dp, zref in ((0, g[f"zeta_{tag}"]), (1, g[f"zeta_dp_{tag}"])):
+            pr = fm.prior_step(omega - 1.0, K, 0, 1.0, 1.0) if not dp else None
+            if dp:  # prior term of update_zeta_dp_cpp from explicit kappa1/kappa2
+                d12 = po.digamma(omega + kappa2)
+                e1, e2 = po.digamma(omega) - d12, po.digamma(kappa2) - d12
+                lp = e1 + np.concatenate([[0.0], np.cumsum(e2)[:-1]])
+            else:
+                lp = pr["logprior"]
+            out = eng.estep(K, lp, T, engine=engine, want_zeta=True)
+            zn = zref / zref.sum(axis=1, keepdims=True)
+            assert out["underflow"] == 0
+            assert np.max(np.abs(out["zeta"] - zn)) < 1e-12
+            np.testing.assert_allclose(out["cs"], zn.sum(axis=0), rtol=1e-12)
+            # M-step statistics and the collapsed expec_log_x
+            st = po.estep_stats(codes, ncat, K, lp - 1.0, T)
+            np.testing.assert_allclose(out["S"], st["S"], rtol=1e-11, atol=1e-12)
+            assert abs(out["H"] - st["H"]) < 1e-10 * max(1.0, abs(st["H"]))
+            if not dp:
+                ex = float(np.sum(out["S"] * T)) + K * int((codes == 0).sum())
+                assert abs(ex - float(g[f"expec_log_x_{tag}"])) < 1e-10 * abs(float(g[f"expec_log_x_{tag}"]))
+
+
+def test_fit_live_oracle_random_shapes():
+    """seeded random shapes, CUDA path vs the literal oracle run live."""
+    rng = np.random.default_rng(7)
+    for case in range(6):
+        J = int(rng.integers(1, 40))
+        ncat = rng.integers(1, 9, size=J).astype(np.int32)
+        K = int(rng.integers(1, 12))
+        dp = case % 2
+        N = int(rng.integers(5, 600))
+        codes, _ = synth.make_codes(100 + case, N, ncat, max(K, 2), p_na=0.15 * (case % 3))
+        z0 = synth.zeta_init(case, N, K)
+        p0 = synth.phi_init(case, ncat, K)
+        ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, dp, 1.0, 1.0, 0.1, 25, 1e-3, z0, p0)
+        for engine in (1, 2):
+            with Engine(codes, ncat) as eng:
+                eng.set_engine(engine)
+                r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), max_iter=25, epsilon=1e-3,
+                            n_cat_bound=int(np.nanmax(po.codes_to_r_matrix(codes))))
+            assert r["n_iter"] == ref["n_iter"]
+            assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+            assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
+            assert np.array_equal(r["pred_class"], ref["pred_class"])
+
+
+def test_predict_consistency(mushroom):
+    """test-mixdir.R:147-152,168-172: predict(res, training rows) == class_prob;
+    predict(all-NA) == lambda (DP: lambda / sum(lambda))."""
+    codes, cats = subset_recode(mushroom["codes"], mushroom["categories"], range(30), range(23))
+    ncat = np.array([len(c) for c in cats], dtype=np.int32)
+    for dp, K in ((False, 3), (True, 10)):
+        z0 = synth.zeta_init(5, 30, K)
+        p0 = synth.phi_init(5, ncat, K)
+        with Engine(codes, ncat) as eng:
+            r = eng.fit(K, z0.sum(axis=0), p0, dp=dp)
+            cp, pc = eng.predict(K, r["lambda_"], r["category_prob"])
+        assert np.max(np.abs(cp - r["class_prob"])) < 1e-12
+        assert np.array_equal(pc, r["pred_class"])
+        with Engine(np.zeros((1, 23), dtype=np.uint8), ncat) as e2:
+            cp0, _ = e2.predict(K, r["lambda_"], r["category_prob"])
+        np.testing.assert_allclose(cp0[0] * r["lambda_"].sum(), r["lambda_"], rtol=1e-12)
+        # and against the oracle's predict
+        ocp, opc = po.predict(po.codes_to_r_matrix(codes), ncat, K, r["lambda_"], r["category_prob"])
+        assert np.max(np.abs(cp - ocp)) < 1e-12
+        assert np.array_equal(pc, opc)
+
+
+@pytest.mark.parametrize("dp", [False, True])
+def test_underflow_is_an_error(dp):
+    """test-mixdir.R:109-114: 50 x 1000 columns -> the zeta-underflow stop()."""
+    ncat = np.full(1000, 2, dtype=np.int32)
+    codes, _ = synth.make_codes(1, 50, ncat, 2)
+    z0 = synth.zeta_init(1, 50, 2)
+    p0 = synth.phi_init(1, ncat, 2)
+    ref = po.fit(po.codes_to_r_matrix(codes), ncat, 2, int(dp), 1.0, 1.0, 0.1, 5, 1e-3, z0, p0)
+    assert ref["status"] == 1
+    for engine in (1, 2):
+        with Engine(codes, ncat) as eng:
+            eng.set_engine(engine)
+            with pytest.raises(ZetaUnderflow, match="underflow in the calculation of zeta"):
+                eng.fit(2, z0.sum(axis=0), p0, dp=dp, max_iter=5)
+
+
+def test_create_from_r_matrix_and_u16():
+    ncat = np.array([300, 4, 7], dtype=np.int32)  # > 255 levels -> 2-byte codes
+    codes, _ = synth.make_codes(9, 500, ncat, 4, p_na=0.1)
+    assert codes.dtype == np.uint16
+    K = 4
+    z0 = synth.zeta_init(2, 500, K)
+    p0 = synth.phi_init(2, ncat, K)
+    ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, 0, 1.0, 1.0, 0.1, 10, 1e-3, z0, p0)
+    for make in (lambda: Engine(codes, ncat),
+                 lambda: Engine.from_r_matrix(po.codes_to_r_matrix(codes), ncat)):
+        for engine in (1, 2):
+            with make() as eng:
+                assert eng.n_missing == int((codes == 0).sum())
+                assert eng.max_code == int(codes.max())
+                eng.set_engine(engine)
+                try:
+                    r = eng.fit(K, z0.sum(axis=0), p0, max_iter=10)
+                except MixdirError as e:
+                    if engine == 2 and "does not fit" in str(e):
+                        continue
+                    raise
+            assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+            assert np.array_equal(r["pred_class"], ref["pred_class"])
+
+
+def test_bad_arguments():
+    codes = np.array([[1, 2], [3, 1]], dtype=np.uint8)
+    with pytest.raises(MixdirError, match="exceeds"):
+        Engine(codes, [2, 2])  # code 3 > C_0 = 2
+    with Engine(codes, [3, 2]) as eng:
+        with pytest.raises(ValueError):
+            eng.fit(2, [1.0, 1.0], np.ones(3))  # wrong phi_init length (R/mixdir_vi.R:41-47)
+        with pytest.raises(MixdirError):
+            eng.fit(1000, np.ones(1000), np.ones(5000))
+
+
+def test_full_size_properties():
+    """BASELINE S4 shape at reduced N (fits the test budget): size-independent invariants +
+    fused vs generic kernel agreement + a row-subsample checked against the oracle."""
+    pat = np.array([16, 12, 8, 4, 2, 10] * 10, dtype=np.int32)
+    N, K = 300_000, 32
+    codes, _ = synth.make_codes(2, N, pat, K)
+    p0 = synth.phi_init(2, pat, K)
+    cs0 = np.full(K, N / K)
+    outs = {}
+    for engine in (1, 2):
+        with Engine(codes, pat) as eng:
+            eng.set_engine(engine)
+            outs[engine] = eng.fit(K, cs0, p0, max_iter=4, epsilon=-np.inf, want_class_prob=False)
+            outs[engine]["timing"] = eng.timing()
+    a, b = outs[1], outs[2]
+    assert rel(a["convergence"], b["convergence"]) < 1e-11
+    np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(a["pred_class"], b["pred_class"])
+    # sum_k colSums(zeta) == N ; sum_r S_jkr summed over k == number of non-NA cells in column j
+    np.testing.assert_allclose(b["omega"].sum(), N + K * 1.0, rtol=1e-12)
+    o = 0
+    for j, c in enumerate(pat):
+        tot = (b["phi"][o:o + K * c] - 0.1).sum()
+        assert abs(tot - N) < 1e-6 * N
+        o += K * c
+    # fused kernel really ran as planned: K=32 needs two CTAs of 16 classes
+    assert b["timing"]["engine"] == 2 and b["timing"]["cluster_size"] >= 1
+    # oracle on the same inputs, literal loop, same init
+    sub = slice(0, 3000)
+    ref = po.fit(po.codes_to_r_matrix(codes[sub]), pat, K, 0, 1.0, 1.0, 0.1, 4, -np.inf,
+                 synth.zeta_init(1, 3000, K), p0)
+    with Engine(codes[sub], pat) as eng:
+        r = eng.fit(K, synth.zeta_init(1, 3000, K).sum(axis=0), p0, max_iter=4, epsilon=-np.inf)
+    assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+    assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
