@@ -190,6 +190,20 @@ double oracle_expec_log_x(const double* X, int n_ind, const double* phia, int cd
   return result;
 }
 
+/* Optional hooks: when set (oracle/_ref installs them, see ref_wrap.cpp
+ * ref_install_hooks), oracle_fit calls the REFERENCE'S OWN native functions
+ * (src/mixdir_impl.cpp compiled verbatim) instead of the restatements above.
+ * That is the "reference" CPU baseline of bench.py. */
+typedef void (*hook_update_zeta_t)(double*, const double*, const double*, int, const double*, int,
+                                   int, int, int);
+typedef void (*hook_update_zeta_dp_t)(double*, const double*, const double*, int, const double*,
+                                      const double*, int, int, int, int);
+typedef double (*hook_expec_log_x_t)(const double*, int, const double*, int, const double*, int,
+                                     int, int);
+hook_update_zeta_t oracle_hook_update_zeta = 0;
+hook_update_zeta_dp_t oracle_hook_update_zeta_dp = 0;
+hook_expec_log_x_t oracle_hook_expec_log_x = 0;
+
 /* ------------------------------------------------------------------------- */
 /* R-level helpers                                                            */
 /* ------------------------------------------------------------------------- */
@@ -424,10 +438,12 @@ int oracle_fit(const double* X, int n_ind, int n_quest, const int* ncat, int n_l
     if (!dp) {
       col_sums(zeta, N, K, omega); /* R/mixdir_vi.R:61 */
       for (int k = 0; k < K; k++) omega[k] += alpha1;
-      oracle_update_zeta(zeta, X, phia, cdim, omega, N, J, K, n_cat); /* :76 */
+      (oracle_hook_update_zeta ? oracle_hook_update_zeta : oracle_update_zeta)(
+          zeta, X, phia, cdim, omega, N, J, K, n_cat); /* :76 */
     } else {
       dp_kappa(zeta, N, K, alpha1, alpha2, omega, kappa2); /* R/mixdir_vi_dp.R:68-71 */
-      oracle_update_zeta_dp(zeta, X, phia, cdim, omega, kappa2, N, J, K, n_cat); /* :90 */
+      (oracle_hook_update_zeta_dp ? oracle_hook_update_zeta_dp : oracle_update_zeta_dp)(
+          zeta, X, phia, cdim, omega, kappa2, N, J, K, n_cat); /* :90 */
     }
     /* underflow guard + normalise (R/mixdir_vi.R:77-82, R/mixdir_vi_dp.R:91-96) */
     int under = 0;
@@ -524,7 +540,8 @@ int oracle_fit(const double* X, int n_ind, int n_quest, const int* ncat, int n_l
       tC = (double)sC;
       tG = (double)sG;
     }
-    tD = oracle_expec_log_x(X, N, phia, cdim, zeta, J, K, n_cat);
+    tD = (oracle_hook_expec_log_x ? oracle_hook_expec_log_x : oracle_expec_log_x)(
+        X, N, phia, cdim, zeta, J, K, n_cat);
     {
       long double sF = 0;
       for (int i = 0; i < N; i++) sF += entrop_zeta_row(zeta, N, K, i);
@@ -570,7 +587,8 @@ int oracle_fit(const double* X, int n_ind, int n_quest, const int* ncat, int n_l
       memcpy(prior_out, omega, K * sizeof(double));
       memcpy(prior_out + K, kappa2, K * sizeof(double));
     }
-    oracle_predict(X, N, J, ncat, K, lambda, U, class_prob, pred_class);
+    if (class_prob) /* NULL: skip the final pass (bench.py times iterations only) */
+      oracle_predict(X, N, J, ncat, K, lambda, U, class_prob, pred_class);
     memcpy(phi_out, phi, nphi * sizeof(double));
   }
   *warn_flags = warn;

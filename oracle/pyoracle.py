@@ -136,8 +136,15 @@ def codes_to_r_matrix(codes):
     return np.asfortranarray(X)
 
 
-def fit(X, ncat, K, dp, alpha1, alpha2, beta, max_iter, epsilon, zeta_init, phi_init):
-    """Literal restatement of mixdir_vi / mixdir_vi_dp; returns a dict like the R result list."""
+def fit(X, ncat, K, dp, alpha1, alpha2, beta, max_iter, epsilon, zeta_init, phi_init,
+        which="oracle", final_pass=True):
+    """Literal restatement of mixdir_vi / mixdir_vi_dp; returns a dict like the R result list.
+    which='ref': same loop, but the three native steps run the reference's own
+    src/mixdir_impl.cpp code (oracle/_ref)."""
+    L = lib()
+    if which == "ref":
+        L = ref()
+        L.ref_install_hooks(1)
     X = _f64(X)
     N, J = X.shape
     ncat = np.ascontiguousarray(ncat, dtype=np.int32)
@@ -148,16 +155,16 @@ def fit(X, ncat, K, dp, alpha1, alpha2, beta, max_iter, epsilon, zeta_init, phi_
     hist = np.full(max(max_iter, 1), np.nan)
     n_iter, conv, warn = C.c_int(0), C.c_int(0), C.c_int(0)
     lam = np.zeros(K)
-    cp = np.zeros((N, K), order="F")
+    cp = np.zeros((N, K), order="F") if final_pass else None
     pc = np.zeros(N, dtype=np.int32)
     U = np.zeros(nphi)
     prior = np.zeros(2 * K)
     phi = np.zeros(nphi)
-    st = lib().oracle_fit(_d(X), N, J, ncat.ctypes.data_as(_ip), K, int(dp), C.c_double(alpha1),
+    st = L.oracle_fit(_d(X), N, J, ncat.ctypes.data_as(_ip), K, int(dp), C.c_double(alpha1),
                           C.c_double(alpha2), C.c_double(beta), int(max_iter), C.c_double(epsilon),
                           _d(zeta_init), _d(phi_init), _d(hist), C.byref(n_iter), C.byref(conv),
-                          _d(lam), _d(cp), pc.ctypes.data_as(_ip), _d(U), _d(prior), _d(phi),
-                          C.byref(warn))
+                          _d(lam), _d(cp) if final_pass else None, pc.ctypes.data_as(_ip), _d(U),
+                   _d(prior), _d(phi), C.byref(warn))
     n = n_iter.value
     out = dict(status=st, converged=bool(conv.value), convergence=hist[:n].copy(),
                ELBO=float(hist[n - 1]) if n else float("nan"), n_iter=n, lambda_=lam,

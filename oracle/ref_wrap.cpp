@@ -55,4 +55,40 @@ void ref_update_zeta_dp(double* zeta, double* X, double* phia, int n_cat_dim, do
   update_zeta_dp_cpp(zm, Xm, ph, k1, k2, n_ind, n_quest, n_latent, n_cat);
 }
 
+// Route oracle_fit's three native steps through the reference's own functions
+// (see the hook declarations in mixdir_oracle.c).  Only meaningful inside
+// oracle/_ref/libmixdir_ref.so, which links both.
+typedef void (*hook_update_zeta_t)(double*, const double*, const double*, int, const double*, int,
+                                   int, int, int);
+typedef void (*hook_update_zeta_dp_t)(double*, const double*, const double*, int, const double*,
+                                      const double*, int, int, int, int);
+typedef double (*hook_expec_log_x_t)(const double*, int, const double*, int, const double*, int,
+                                     int, int);
+extern hook_update_zeta_t oracle_hook_update_zeta;
+extern hook_update_zeta_dp_t oracle_hook_update_zeta_dp;
+extern hook_expec_log_x_t oracle_hook_expec_log_x;
+
+static void hk_update_zeta(double* zeta, const double* X, const double* phia, int cdim,
+                           const double* omega, int n_ind, int n_quest, int n_latent, int n_cat) {
+  ref_update_zeta(zeta, const_cast<double*>(X), const_cast<double*>(phia), cdim,
+                  const_cast<double*>(omega), n_ind, n_quest, n_latent, n_cat);
+}
+static void hk_update_zeta_dp(double* zeta, const double* X, const double* phia, int cdim,
+                              const double* k1, const double* k2, int n_ind, int n_quest,
+                              int n_latent, int n_cat) {
+  ref_update_zeta_dp(zeta, const_cast<double*>(X), const_cast<double*>(phia), cdim,
+                     const_cast<double*>(k1), const_cast<double*>(k2), n_ind, n_quest, n_latent,
+                     n_cat);
+}
+static double hk_expec_log_x(const double* X, int n_ind, const double* phia, int cdim,
+                             const double* zeta, int n_quest, int n_latent, int n_cat) {
+  return ref_expec_log_x(const_cast<double*>(X), n_ind, n_quest, const_cast<double*>(phia), cdim,
+                         const_cast<double*>(zeta), n_latent, n_cat);
+}
+void ref_install_hooks(int on) {
+  oracle_hook_update_zeta = on ? hk_update_zeta : nullptr;
+  oracle_hook_update_zeta_dp = on ? hk_update_zeta_dp : nullptr;
+  oracle_hook_expec_log_x = on ? hk_expec_log_x : nullptr;
+}
+
 }  // extern "C"

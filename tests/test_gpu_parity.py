@@ -163,9 +163,20 @@ def test_underflow_is_an_error(dp):
     assert ref["status"] == 1
     for engine in (1, 2):
         with Engine(codes, ncat) as eng:
-            eng.set_engine(engine)
+            # J=1000 features do not fit the fused kernel's shared-memory plan: engine 0 picks
+            # the generic kernel by itself, engine 2 (forced) must say so
+            eng.set_engine(0 if engine == 2 else 1)
             with pytest.raises(ZetaUnderflow, match="underflow in the calculation of zeta"):
                 eng.fit(2, z0.sum(axis=0), p0, dp=dp, max_iter=5)
+    # a shape that does fit the fused kernel: few features, many categories -> tiny T values
+    ncat2 = np.full(40, 2, dtype=np.int32)
+    codes2, _ = synth.make_codes(1, 64, ncat2, 2)
+    p_big = synth.phi_init(1, ncat2, 2).copy()
+    p_big[::2] = 1e-300  # psi(1e-300) ~ -1e300: every logit underflows
+    with Engine(codes2, ncat2) as eng:
+        eng.set_engine(2)
+        with pytest.raises(ZetaUnderflow):
+            eng.fit(2, [32.0, 32.0], p_big, dp=dp, max_iter=3)
 
 
 def test_create_from_r_matrix_and_u16():
