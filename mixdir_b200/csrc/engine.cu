@@ -19,6 +19,7 @@
 
 #include "../../include/mixdir_b200.h"
 #include "kernels.cuh"
+#include "fused.cuh"
 
 using namespace mxd;
 

@@ -719,342 +719,4 @@ __global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
     if (a.pred_class && lane == 0) a.pred_class[row] = (bi == 0x7fffffff) ? 0 : bi + 1;
   }
 }
-
-// ---------------------------------------------------------------------------
-// FUSED E+M pass (the hot kernel).  See DESIGN.md "Fused kernel".
-//
-//  * persistent thread-block clusters of P CTAs; CTA `rank` owns the KC classes
-//    [rank*KC, rank*KC+KC): its slice of the table T and of the statistics S
-//    lives in shared memory for the whole launch (no atomics anywhere).
-//  * lanes = classes: a warp instruction covers RPW = 32/KC rows ("slots").
-//  * row tiles arrive through the TMA engine (cp.async.bulk + mbarrier),
-//    double buffered; every CTA of the cluster pulls the same tile (the second
-//    read is an L2 hit).
-//  * E-step: per row, J table gathers from shared memory, added in feature
-//    order exactly like mixdir_impl.cpp:77-82; soft-max over the classes with
-//    warp shuffles inside the CTA and one (max, sum) exchange over distributed
-//    shared memory across the cluster.
-//  * M-step: warps own rows; the features are cut into G word-groups and warp w
-//    works on group (w + t) mod G at step t, with a block barrier between
-//    steps, so no two warps ever touch the same histogram rows; the slots of a
-//    warp rotate the byte order so they never share a feature either.  Plain
-//    shared-memory read-modify-write, fp64.
-//  * flush: per-cluster partials to global, reduced in fixed order by
-//    k_reduce_partials (bit-reproducible run to run).
-// ---------------------------------------------------------------------------
-struct FusedArgs {
-  const uint32_t* codes;  // [n_rows + kRowPad][WPR]
-  int64_t n_rows;
-  int n_tiles;
-  int WPR;
-  int NR;
-  int K, KP;
-  int P;                  // cluster size
-  const int* rowoff_pad;  // [WPR*FPW]: category-row offset per (padded) feature
-  const double* T;
-  const double* logprior;
-  double* Spart;
-  double* cspart;
-  double* Hpart;
-  int* underflow;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-template <int FPW>
-__device__ __forceinline__ void load_ro(const int* ro_s, int w, int* ro) {
-  if constexpr (FPW == 4) {
-    const int4 r = reinterpret_cast<const int4*>(ro_s)[w];
-    ro[0] = r.x; ro[1] = r.y; ro[2] = r.z; ro[3] = r.w;
-  } else {
-    const int2 r = reinterpret_cast<const int2*>(ro_s)[w];
-    ro[0] = r.x; ro[1] = r.y;
-  }
-}
-
-template <int KC, int CB, int RG>
-struct FusedCfg {
-  static constexpr int RPW = 32 / KC;  // rows per warp instruction
-  static constexpr int FPW = 4 / CB;   // features per 32-bit code word
-  static_assert(RPW <= FPW, "slots of a warp must be able to take distinct features of a word");
-};
-
-// dynamic shared memory carve-up, shared by host (sizing) and device
-struct FusedSmem {
-  size_t off_T, off_S, off_tile, off_exch, off_ro, off_red, off_bar, total;
-  __host__ __device__ FusedSmem(int NR, int KC, int W, int RG, int WPR, int FPW, int P) {
-    const int RPW = 32 / KC;
-    const size_t R = (size_t)W * RG * RPW;
-    size_t o = 0;
-    off_T = o;     o += (size_t)NR * KC * 8;
-    off_S = o;     o += (size_t)NR * KC * 8;
-    off_tile = o;  o += 2 * R * WPR * 4;
-    o = (o + 15) & ~(size_t)15;
-    off_exch = o;  o += (P > 1) ? 2 * R * P * 16 : 0;
-    off_ro = o;    o += (size_t)WPR * FPW * 4;
-    o = (o + 15) & ~(size_t)15;
-    off_red = o;   o += (size_t)(W * KC + W) * 8;
-    off_bar = o;   o += 16;
-    total = o;
-  }
-};
-
-template <int KC, int CB, int RG>
-__global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
-  using Cfg = FusedCfg<KC, CB, RG>;
-  constexpr int RPW = Cfg::RPW, FPW = Cfg::FPW;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-
-  cg::cluster_group cluster = cg::this_cluster();
-  const int P = a.P;
-  const int rank = (P > 1) ? (int)cluster.block_rank() : 0;
-  const int cluster_id = blockIdx.x / P;
-  const int n_clusters = gridDim.x / P;
-  const int W = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = lane / KC, kc = lane % KC;
-  const int kg = rank * KC + kc;  // global (padded) class index of this lane
-  const int WPR = a.WPR, NR = a.NR, KP = a.KP;
-  const int R = W * RG * RPW;  // rows per tile
-
-  const FusedSmem L(NR, KC, W, RG, WPR, FPW, P);
-  double* T_s = reinterpret_cast<double*>(smem_raw + L.off_T);
-  double* S_s = reinterpret_cast<double*>(smem_raw + L.off_S);
-  uint32_t* tile_s = reinterpret_cast<uint32_t*>(smem_raw + L.off_tile);
-  double2* exch_s = reinterpret_cast<double2*>(smem_raw + L.off_exch);
-  int* ro_s = reinterpret_cast<int*>(smem_raw + L.off_ro);
-  double* red_s = reinterpret_cast<double*>(smem_raw + L.off_red);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
-
-  const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
-
-  // ---- prologue: barriers, first tile in flight, tables into shared memory ----
-  if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && cluster_id < a.n_tiles) {
-    mbar_expect_tx(&bar[0], tile_bytes);
-    tma_load_1d(tile_s, a.codes + (size_t)cluster_id * R * WPR, tile_bytes, &bar[0]);
-  }
-  for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
-    const int g = i / KC, c = i - g * KC;
-    T_s[i] = a.T[(size_t)g * KP + rank * KC + c];
-    S_s[i] = 0.0;
-  }
-  for (int i = threadIdx.x; i < WPR * FPW; i += blockDim.x) ro_s[i] = a.rowoff_pad[i] * KC;
-  const double lp = a.logprior[kg];
-  const bool kreal = kg < a.K;
-  __syncthreads();
-  if (P > 1) cluster.sync();  // every CTA of the cluster is resident before DSMEM traffic
-
-  const double* Tl = T_s + kc;
-  double* Sl = S_s + kc;
-  double csacc = 0, hacc = 0;
-  int uflag = 0;
-  const double kTiny = DBL_MIN * log(DBL_MIN);
-  const int row_in_tile0 = warp * RG * RPW + slot;  // + rg*RPW
-
-  int it = 0;
-  for (int t = cluster_id; t < a.n_tiles; t += n_clusters, ++it) {
-    const int buf = it & 1;
-    const uint32_t* tile = tile_s + (size_t)buf * R * WPR;
-    // prefetch the next tile of this cluster into the other buffer (its last
-    // readers finished at the closing barrier of the previous iteration)
-    if (threadIdx.x == 0 && t + n_clusters < a.n_tiles) {
-      mbar_expect_tx(&bar[buf ^ 1], tile_bytes);
-      tma_load_1d(tile_s + (size_t)(buf ^ 1) * R * WPR,
-                  a.codes + (size_t)(t + n_clusters) * R * WPR, tile_bytes, &bar[buf ^ 1]);
-    }
-    mbar_wait(&bar[buf], (it >> 1) & 1);
-
-    // ---- E-step gather: acc[rg] = sum_j T[j, x_ij, k] in feature order ----
-    double acc[RG];
-#pragma unroll
-    for (int rg = 0; rg < RG; rg++) acc[rg] = 0.0;
-    const uint32_t* trow = tile + (size_t)row_in_tile0 * WPR;
-    for (int w = 0; w < WPR; w++) {
-      int ro[FPW];
-      load_ro<FPW>(ro_s, w, ro);
-#pragma unroll
-      for (int rg = 0; rg < RG; rg++) {
-        const uint32_t cw = trow[(size_t)rg * RPW * WPR + w];
-#pragma unroll
-        for (int f = 0; f < FPW; f++) {
-          const uint32_t x = CB == 1 ? ((cw >> (8 * f)) & 0xffu) : ((cw >> (16 * f)) & 0xffffu);
-          acc[rg] += Tl[ro[f] + (int)x * KC];
-        }
-      }
-    }
-
-    // ---- soft-max over classes (R/mixdir_vi.R:82), cluster-wide ----
-    double lg[RG], z[RG], mloc[RG];
-#pragma unroll
-    for (int rg = 0; rg < RG; rg++) {
-      const double l = (lp + acc[rg]) - 1.0;  // mixdir_impl.cpp:83 / :148
-      double m = l;
-#pragma unroll
-      for (int o = KC / 2; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const double e = (l == -INFINITY) ? 0.0 : exp(l - m);
-      double s = e;
-#pragma unroll
-      for (int o = KC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      lg[rg] = l;
-      mloc[rg] = m;
-      z[rg] = e;
-      acc[rg] = s;  // reuse: local sum
-    }
-    if (P > 1) {
-      double2* ex = exch_s + (size_t)buf * R * P;
-#pragma unroll
-      for (int rg = 0; rg < RG; rg++) {
-        if (kc < P) {
-          double2* dst = cluster.map_shared_rank(&ex[(size_t)(row_in_tile0 + rg * RPW) * P + rank], kc);
-          *dst = make_double2(mloc[rg], acc[rg]);
-        }
-      }
-      cluster.sync();
-#pragma unroll
-      for (int rg = 0; rg < RG; rg++) {
-        double mp = -INFINITY, sp = 0.0;
-        if (kc < P) {
-          const double2 v = ex[(size_t)(row_in_tile0 + rg * RPW) * P + kc];
-          mp = v.x;
-          sp = v.y;
-        }
-        double M = mp;
-#pragma unroll
-        for (int o = KC / 2; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
-        double term = (kc < P && mp != -INFINITY) ? sp * exp(mp - M) : 0.0;
-#pragma unroll
-        for (int o = KC / 2; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
-        // rescale the local exponentials to the cluster-wide maximum
-        z[rg] = (mloc[rg] == -INFINITY) ? 0.0 : z[rg] * exp(mloc[rg] - M);
-        mloc[rg] = M;
-        acc[rg] = term;
-      }
-    }
-#pragma unroll
-    for (int rg = 0; rg < RG; rg++) {
-      const int64_t grow = (int64_t)t * R + row_in_tile0 + rg * RPW;
-      const bool valid = grow < a.n_rows;
-      const double M = mloc[rg], stot = acc[rg];
-      double zz = 0.0;
-      if (valid) {
-        if (M < kExpUnderflow) uflag = 1;  // rowSums(zeta) == 0  (R/mixdir_vi.R:77)
-        if (kreal) {
-          zz = z[rg] / stot;
-          hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - log(stot)) : kTiny;  // R/mixdir_vi.R:181
-          csacc += zz;
-        }
-      }
-      z[rg] = zz;
-    }
-
-    // ---- M-step scatter: rotating feature-group schedule, no atomics ----
-    // Warp w works on code word (w + step) mod WPR, so no two warps share a
-    // feature between two block barriers.  Inside a warp the RPW slots (rows)
-    // start SB features apart in the word and advance in batches of SB features,
-    // so in every batch the slots touch disjoint features; the SB read-modify-
-    // writes of a batch are independent and overlap.
-    constexpr int SB = FPW / RPW;
-    for (int step = 0; step < WPR; step++) {
-      int g = warp + step;
-      if (g >= WPR) g -= WPR;
-      int ro0[FPW], ro[FPW];
-      load_ro<FPW>(ro_s, g, ro0);
-#pragma unroll
-      for (int f = 0; f < FPW; f++) {
-        ro[f] = ro0[f];
-#pragma unroll
-        for (int sl = 1; sl < RPW; sl++)
-          if (slot == sl) ro[f] = ro0[(f + SB * sl) % FPW];
-      }
-#pragma unroll
-      for (int rg = 0; rg < RG; rg++) {
-        uint32_t cw = trow[(size_t)rg * RPW * WPR + g];
-        cw = __funnelshift_r(cw, cw, (8 * CB * SB * slot) & 31);
-#pragma unroll
-        for (int b = 0; b < RPW; b++) {
-          int idx[SB];
-          double v[SB];
-#pragma unroll
-          for (int f = 0; f < SB; f++) {
-            const int ff = b * SB + f;
-            const uint32_t x = CB == 1 ? ((cw >> (8 * ff)) & 0xffu) : ((cw >> (16 * ff)) & 0xffffu);
-            idx[f] = ro[ff] + (int)x * KC;
-            v[f] = Sl[idx[f]];
-          }
-#pragma unroll
-          for (int f = 0; f < SB; f++) Sl[idx[f]] = v[f] + z[rg];
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  // ---- flush: this CTA's class slice of S, class masses, entropy ----
-  {
-    double* Sp = a.Spart + (size_t)cluster_id * NR * KP;
-    for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
-      const int g = i / KC, c = i - g * KC;
-      Sp[(size_t)g * KP + rank * KC + c] = S_s[i];
-    }
-#pragma unroll
-    for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);
-    hacc = warp_sum(hacc);
-    if (slot == 0) red_s[warp * KC + kc] = csacc;
-    if (lane == 0) red_s[W * KC + warp] = hacc;
-    __syncthreads();
-    if (threadIdx.x < KC) {
-      double s = 0;
-      for (int w = 0; w < W; w++) s += red_s[w * KC + threadIdx.x];
-      a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x] = s;
-    }
-    if (threadIdx.x == 0) {
-      double h = 0;
-      for (int w = 0; w < W; w++) h += red_s[W * KC + w];
-      a.Hpart[blockIdx.x] = h;
-    }
-    if (uflag) atomicExch(a.underflow, 1);
-  }
-  if (P > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
-}
-
 }  // namespace mxd

@@ -1,0 +1,75 @@
+"""CPU tests of the host-side mirror of mixdir()'s input handling (R/mixdir.R:91-118,
+R/predict.R:64-84) and of the deterministic synthetic generators."""
+import numpy as np
+import pytest
+
+from mixdir_b200 import synth
+from mixdir_b200.coding import MISSING_LEVEL, code_columns, recode_for_predict
+
+
+def test_factor_coding_sorted_levels_and_na():
+    cols = [["b", "a", None, "c", "a"], ["x", "x", "x", float("nan"), "x"]]
+    codes, cats = code_columns(cols)
+    assert cats == [["a", "b", "c"], ["x"]]
+    assert codes.dtype == np.uint8
+    assert codes.tolist() == [[2, 1], [1, 1], [0, 1], [3, 0], [1, 1]]
+
+
+def test_na_handle_category_adds_level_to_every_column():
+    """R/mixdir.R:103-106: "(Missing)" is appended to EVERY column."""
+    cols = [["b", "a", None], ["x", "y", "x"]]
+    codes, cats = code_columns(cols, na_handle="category")
+    assert cats == [["a", "b", MISSING_LEVEL], ["x", "y", MISSING_LEVEL]]
+    assert codes.tolist() == [[2, 1], [1, 2], [3, 1]]
+    assert (codes != 0).all()
+
+
+def test_empty_column_is_an_error():
+    with pytest.raises(ValueError, match="is empty"):  # R/mixdir.R:112-115
+        code_columns([[None, None]])
+    with pytest.raises(ValueError):
+        code_columns([["a"]], na_handle="bogus")  # match.arg
+
+
+def test_numeric_input_is_coded_by_its_string_form():
+    # create_data() passes a numeric matrix; mixdir() does as.factor(as.character(col))
+    codes, cats = code_columns([[1, 3, 1, 3], [2, 2, 3, 2]])
+    assert cats == [["1", "3"], ["2", "3"]] and codes.tolist() == [[1, 1], [2, 1], [1, 2], [2, 1]]
+
+
+def test_wide_features_use_two_byte_codes():
+    col = [str(i).zfill(4) for i in range(300)]
+    codes, cats = code_columns([col])
+    assert codes.dtype == np.uint16 and codes.max() == 300
+
+
+def test_recode_for_predict_missing_column_and_unseen_level():
+    names, cats = ["f1", "f2"], [["a", "b"], ["x", "y"]]
+    codes, unseen = recode_for_predict({"f2": ["y", "zzz", None]}, names, cats)
+    assert codes.tolist() == [[0, 2], [0, 0], [0, 0]]  # missing column -> NA, unseen -> NA
+    assert unseen == {"f2": {"zzz"}}
+    codes, unseen = recode_for_predict({"f1": [None]}, names, [c + [MISSING_LEVEL] for c in cats],
+                                       na_handle="category")
+    assert codes.tolist() == [[3, 0]] and not unseen
+
+
+def test_synth_is_a_pure_function_of_seed_and_row():
+    ncat = np.array([4, 2, 9], dtype=np.int32)
+    full, z = synth.make_codes(3, 1000, ncat, 5, p_na=0.2)
+    part, z2 = synth.make_codes(3, 300, ncat, 5, p_na=0.2, row0=500)
+    assert np.array_equal(full[500:800], part) and np.array_equal(z[500:800], z2)
+    assert full.max() <= 9 and (full[:, 1] <= 2).all()
+    assert 0.15 < (full == 0).mean() < 0.25
+    zi = synth.zeta_init(1, 50, 7)
+    np.testing.assert_allclose(zi.sum(axis=1), 1.0)
+    assert np.array_equal(synth.zeta_init(1, 20, 7, row0=30), zi[30:])
+    p = synth.phi_init(1, ncat, 7)
+    assert set(np.unique(p)) <= {1.0, 2.0, 3.0} and p.size == 7 * 15
+
+
+def test_toy_data_matches_helper_r():
+    t = synth.TOY_DATA
+    assert t.shape == (10, 3)
+    assert (t[1] == 3).all() and (t[6] == 3).all()          # rows 2, 7 = CCC
+    for i in (4, 5, 7, 8, 9):
+        assert t[i].tolist() == [1, 2, 2]                   # rows 5,6,8,9,10 = ABB
