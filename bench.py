@@ -196,7 +196,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from mixdir_b200 import Engine, synth
+    from mixdir_b200 import Comm, Engine, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,7 +243,8 @@ def run_ours(args):
 
     cs0 = np.full(K, N * world / K)
     p0 = synth.phi_init(2, ncat, K)
-    mk = lambda: Engine(codes_np, ncat, dist=(local, rank, world, uid))  # noqa: E731
+    comm = Comm(local, rank, world, uid)  # one NCCL communicator, shared by every handle below
+    mk = lambda: Engine(codes_np, ncat, dist=comm)  # noqa: E731
 
     # ---- value: device-resident, K iterations, CUDA events inside the engine ----
     eng = mk()

@@ -97,13 +97,20 @@ int mixdir_b200_create_from_r_matrix(const double* X, int64_t n_rows, int n_feat
                                      const int* ncat, int n_devices, const int* device_ids,
                                      mixdir_b200_handle** out);
 
-/* Multi-process flavour (one process per GPU, e.g. torchrun): every rank passes
- * its own contiguous row shard.  unique_id is the 128-byte NCCL id produced by
- * mixdir_b200_nccl_unique_id() on rank 0 and broadcast by the host program. */
+/* Multi-process flavour (one process per GPU, e.g. torchrun): every rank passes its own
+ * contiguous row shard.  The NCCL communicator lives in a separate object so that it is set up
+ * once and shared by any number of handles (repetitions, predict, re-uploads):
+ * unique_id is the 128-byte NCCL id produced by mixdir_b200_nccl_unique_id() on rank 0 and
+ * broadcast by the host program; comm_init is collective over all ranks.  The communicator
+ * must outlive the handles created on it. */
+typedef struct mixdir_b200_comm mixdir_b200_comm;
 int mixdir_b200_nccl_unique_id(void* out128);
+int mixdir_b200_comm_init(int device, int rank, int world, const void* unique_id128,
+                          mixdir_b200_comm** out);
+int mixdir_b200_comm_destroy(mixdir_b200_comm* comm);
 int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_rows_local,
-                            int n_features, const int* ncat, int device, int rank, int world,
-                            const void* unique_id128, mixdir_b200_handle** out);
+                            int n_features, const int* ncat, mixdir_b200_comm* comm,
+                            mixdir_b200_handle** out);
 
 int mixdir_b200_destroy(mixdir_b200_handle* h);
 

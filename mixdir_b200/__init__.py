@@ -5,4 +5,4 @@ package is the host-side mirror of the reference's R interface for that path.
 """
 from .api import mixdir, predict  # noqa: F401
 from .coding import code_columns, recode_for_predict  # noqa: F401
-from .engine import Engine, MixdirError, ZetaUnderflow  # noqa: F401
+from .engine import Comm, Engine, MixdirError, ZetaUnderflow  # noqa: F401

@@ -129,6 +129,7 @@ struct Shard {
   int64_t* d_ragoff = nullptr;
   uint8_t* d_na_row = nullptr;
   nccl::comm_t comm = nullptr;
+  bool owns_comm = true;
   int sm_count = 0, smem_optin = 0;
   // workspace (sized for ws_K / ws_KP)
   int ws_K = 0, ws_KP = 0, ws_iter = 0, ws_clusters = 0, ws_ctas = 0;
@@ -212,7 +213,7 @@ static void free_shard(Shard& s) {
   if (s.ev_loop0) cudaEventDestroy(s.ev_loop0);
   if (s.ev_loop1) cudaEventDestroy(s.ev_loop1);
   s.ev_loop0 = s.ev_loop1 = nullptr;
-  if (s.comm && nccl::lib) nccl::CommDestroy(s.comm);
+  if (s.comm && s.owns_comm && nccl::lib) nccl::CommDestroy(s.comm);
   s.comm = nullptr;
   if (s.stream) cudaStreamDestroy(s.stream);
   s.stream = nullptr;
@@ -471,37 +472,73 @@ extern "C" int mixdir_b200_nccl_unique_id(void* out128) {
   return MIXDIR_B200_OK;
 }
 
-extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_rows_local,
-                                       int n_features, const int* ncat, int device, int rank,
-                                       int world, const void* unique_id128,
-                                       mixdir_b200_handle** out) {
+struct mixdir_b200_comm {
+  int device = 0, rank = 0, world = 1;
+  nccl::comm_t comm = nullptr;
+};
+
+extern "C" int mixdir_b200_comm_init(int device, int rank, int world, const void* unique_id128,
+                                     mixdir_b200_comm** out) {
   if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad rank/world");
   if (world > 1 && !unique_id128) return fail(MIXDIR_B200_BAD_ARGUMENT, "unique_id128 is NULL");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(MIXDIR_B200_CUDA_ERROR, "no CUDA device available (mixdir_b200 has no CPU path)");
+  if (device < 0 || device >= count) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad device");
+  mixdir_b200_comm* c = new mixdir_b200_comm();
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  if (world > 1) {
+    int st = nccl::load();
+    if (st != MIXDIR_B200_OK) {
+      delete c;
+      return st;
+    }
+    cudaSetDevice(device);
+    nccl::unique_id id;
+    memcpy(&id, unique_id128, sizeof id);
+    int r = nccl::CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) {
+      delete c;
+      return fail(MIXDIR_B200_CUDA_ERROR, std::string("ncclCommInitRank: ") + nccl::GetErrorString(r));
+    }
+  }
+  *out = c;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_comm_destroy(mixdir_b200_comm* c) {
+  if (!c) return MIXDIR_B200_OK;
+  if (c->comm && nccl::lib) nccl::CommDestroy(c->comm);
+  delete c;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_rows_local,
+                                       int n_features, const int* ncat, mixdir_b200_comm* comm,
+                                       mixdir_b200_handle** out) {
+  if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (!comm) return fail(MIXDIR_B200_BAD_ARGUMENT, "comm is NULL");
   if (n_rows_local < 0 || (n_rows_local > 0 && !codes_local))
     return fail(MIXDIR_B200_BAD_ARGUMENT, "codes_local is NULL");
   mixdir_b200_handle* h = new mixdir_b200_handle();
-  h->rank = rank;
-  h->world = world;
+  h->rank = comm->rank;
+  h->world = comm->world;
   int st = init_geometry(h, code_bytes, n_features, ncat);
   auto body = [&]() -> int {
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-      return fail(MIXDIR_B200_CUDA_ERROR, "no CUDA device available (mixdir_b200 has no CPU path)");
     h->n_rows = n_rows_local;
     h->shards.resize(1);
     Shard& s = h->shards[0];
-    s.device = device;
+    s.device = comm->device;
     s.row0 = 0;
     s.n_rows = n_rows_local;
+    s.comm = comm->comm;
+    s.owns_comm = false;
     RET_IF(init_shard_static(h, s));
-    if (world > 1) {
-      RET_IF(nccl::load());
-      nccl::unique_id id;
-      memcpy(&id, unique_id128, sizeof id);
-      NCCL_TRY(nccl::CommInitRank(&s.comm, world, id, rank));
-    }
     RET_IF(upload_codes(h, s, (const uint8_t*)codes_local));
     return scan_codes(h);
   };

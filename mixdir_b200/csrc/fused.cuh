@@ -99,6 +99,21 @@ __device__ __forceinline__ double lds_f64_ordered(uint32_t addr) {
 __device__ __forceinline__ void sts_f64_ordered(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+// predicated forms: lanes with on == 0 issue no shared-memory traffic
+__device__ __forceinline__ double lds_f64_ordered_if(uint32_t addr, uint32_t on) {
+  double v = 0.0;
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.f64 %0, [%1];\n}\n"
+      : "+d"(v)
+      : "r"(addr), "r"(on)
+      : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64_ordered_if(uint32_t addr, double v, uint32_t on) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f64 [%0], %1;\n}\n" ::"r"(addr),
+               "d"(v), "r"(on)
+               : "memory");
+}
 
 // code f of a 32-bit code word (CB bytes per code), zero extended: one PRMT
 template <int CB>
@@ -199,6 +214,10 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
   double csacc = 0, hacc = 0;
   int uflag = 0;
   const double kTiny = DBL_MIN * log(DBL_MIN);
+  // A slot (row x this CTA's classes) whose responsibilities are all below 2^-100 is skipped by
+  // the M-step: over <= 2^31 rows such terms add up to < 2^-69, far below half an ulp of
+  // phi = S + beta >= beta (R/mixdir_vi.R:88), so phi is unchanged bit for bit.
+  const double kDeadZ = 7.888609052210118e-31;
   const int wrow0 = warp * RW;              // first row of this warp inside the tile
   const int row_in_tile0 = wrow0 + slot;    // + rg*RPW
   const unsigned slot_mask = (KC == 32) ? 0xffffffffu : (((1u << KC) - 1u) << (slot * KC));
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
     else
       __syncwarp();
     // owner lanes: one lane per row finishes the row-level scalars once
+    uint32_t alive = 0;  // bit rg: some class of this lane's slot has a non-negligible zeta
     double M_o = -INFINITY, f_o = 0.0, logs_o = 0.0;
     if (lane < RW) {
       const double2* e = ex + (size_t)(wrow0 + lane) * P;
@@ -309,6 +329,7 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
         csacc += zz;
       }
       ez[rg] = zz;
+      if (__ballot_sync(0xffffffffu, zz > kDeadZ) & slot_mask) alive |= 1u << rg;
     }
 
     // ---- M-step scatter: rotating feature-group schedule, no atomics ----
@@ -334,6 +355,7 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
       }
 #pragma unroll
       for (int rg = 0; rg < RG; rg++) {
+        const uint32_t on = (alive >> rg) & 1u;
 #pragma unroll
         for (int b = 0; b < RPW; b++) {
           uint32_t ad[SB];
@@ -341,10 +363,10 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
 #pragma unroll
           for (int f = 0; f < SB; f++) {
             ad[f] = sb[b * SB + f] + code_of<CB>(cw[rg], b * SB + f) * ROWB;
-            v[f] = lds_f64_ordered(ad[f]);
+            v[f] = lds_f64_ordered_if(ad[f], on);
           }
 #pragma unroll
-          for (int f = 0; f < SB; f++) sts_f64_ordered(ad[f], v[f] + ez[rg]);
+          for (int f = 0; f < SB; f++) sts_f64_ordered_if(ad[f], v[f] + ez[rg], on);
           __syncwarp();
         }
       }

@@ -43,13 +43,36 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class Comm:
+    """NCCL communicator for the one-process-per-GPU flavour (mixdir_b200_comm_init);
+    collective over all ranks, shared by any number of Engine handles."""
+
+    def __init__(self, device, rank, world, unique_id=None):
+        self._c = C.c_void_p()
+        uid = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(_capi.lib().mixdir_b200_comm_init(int(device), int(rank), int(world), uid,
+                                                 C.byref(self._c)))
+        self.device, self.rank, self.world = device, rank, world
+
+    def close(self):
+        if getattr(self, "_c", None) is not None and self._c:
+            _capi.lib().mixdir_b200_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One uploaded code matrix (the `X` of mixdir_vi, /root/reference/R/mixdir_vi.R:2)."""
 
     def __init__(self, codes, ncat, devices=None, dist=None):
         """codes: [N, J] uint8/uint16, 0 = NA.  ncat: C_j per feature.
         devices: list of CUDA device ids for the single-process multi-GPU flavour.
-        dist: (device, rank, world, unique_id_bytes) for the one-process-per-GPU flavour."""
+        dist: a Comm for the one-process-per-GPU flavour (codes = this rank's row shard)."""
         L = _capi.lib()
         codes = np.ascontiguousarray(codes)
         if codes.dtype not in (np.uint8, np.uint16):
@@ -63,11 +86,9 @@ class Engine:
         self._h = C.c_void_p()
         ip = self.ncat.ctypes.data_as(C.POINTER(C.c_int))
         if dist is not None:
-            device, rank, world, uid = dist
-            uid_buf = (C.c_char * 128).from_buffer_copy(uid) if uid is not None else None
+            self._comm = dist  # keep the communicator alive as long as the handle
             st = L.mixdir_b200_create_dist(_ptr(codes), codes.dtype.itemsize, self.n_rows,
-                                           self.n_features, ip, device, rank, world, uid_buf,
-                                           C.byref(self._h))
+                                           self.n_features, ip, dist._c, C.byref(self._h))
         else:
             dev = None if devices is None else (C.c_int * len(devices))(*devices)
             st = L.mixdir_b200_create(_ptr(codes), codes.dtype.itemsize, self.n_rows,

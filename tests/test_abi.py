@@ -58,7 +58,9 @@ def test_argument_checks_do_not_need_a_gpu():
     assert L.mixdir_b200_create(p, 1, 3, 2, bad, 0, None, C.byref(h)) == _capi.BAD_ARGUMENT
     big = (C.c_int * 2)(2, 300)
     assert L.mixdir_b200_create(p, 1, 3, 2, big, 0, None, C.byref(h)) == _capi.BAD_ARGUMENT
-    assert L.mixdir_b200_create_dist(p, 1, 3, 2, ncat, 0, 5, 2, None, C.byref(h)) == _capi.BAD_ARGUMENT
+    c = C.c_void_p()
+    assert L.mixdir_b200_comm_init(0, 5, 2, None, C.byref(c)) == _capi.BAD_ARGUMENT  # rank >= world
+    assert L.mixdir_b200_create_dist(p, 1, 3, 2, ncat, None, C.byref(h)) == _capi.BAD_ARGUMENT
     assert not h
 
 
