@@ -42,6 +42,8 @@ C_PATTERN = [16, 12, 8, 4, 2, 10]  # S4 categories per feature, re
 
 
 def workload(args):
+    if args.cats > 0:  # uniform number of categories (e.g. S3: 10 per feature)
+        return np.full(args.features, args.cats, dtype=np.int32)
     ncat = np.array((C_PATTERN * ((args.features + 5) // 6))[:args.features], dtype=np.int32)
     return ncat
 
@@ -182,7 +184,7 @@ def run_reference(args):
 
 def config_dict(args, ncat):
     return {"workload": f"synthetic {args.rows} x {args.features} per GPU, C_j pattern "
-                        f"{C_PATTERN} (sum C_j = {int(ncat.sum())}), K={args.k}, fixed-K Dirichlet "
+                        f"{C_PATTERN if args.cats <= 0 else args.cats} (sum C_j = {int(ncat.sum())}), K={args.k}, fixed-K Dirichlet "
                         "variant, alpha=1, beta=0.1, p_NA=%g" % args.p_na,
             "rows_per_gpu": args.rows, "features": args.features, "n_latent": args.k,
             "code_bytes": 1 if ncat.max() <= 255 else 2,
@@ -356,6 +358,7 @@ def main():
     ap.add_argument("--features", type=int, default=60)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--p-na", dest="p_na", type=float, default=0.0)
+    ap.add_argument("--cats", type=int, default=0, help="uniform categories per feature (0: S4 pattern)")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
     ap.add_argument("--cpu-rows", dest="cpu_rows", type=int, default=20000)

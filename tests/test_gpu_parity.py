@@ -250,3 +250,26 @@ def test_full_size_properties():
         r = eng.fit(K, synth.zeta_init(1, 3000, K).sum(axis=0), p0, max_iter=4, epsilon=-np.inf)
     assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
     assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
+
+
+@pytest.mark.parametrize("K,J,dp", [(64, 100, 0), (64, 100, 1), (40, 30, 0), (20, 23, 1), (5, 3, 0),
+                                    (1, 4, 0), (33, 7, 1), (128, 12, 0), (256, 5, 0)])
+def test_cluster_shapes_against_oracle(K, J, dp):
+    """every cluster plan of the fused kernel (KC in {8,16,32}, P = 1..8, incl. the S5 shape
+    K=64, J=100 -> 8 CTAs x 8 classes) and large K against the literal oracle."""
+    pat = np.array(([16, 12, 8, 4, 2, 10] * 20)[:J], dtype=np.int32)
+    N = 1500
+    codes, _ = synth.make_codes(11, N, pat, min(K, 16), p_na=0.05)
+    z0 = synth.zeta_init(3, N, K)
+    p0 = synth.phi_init(3, pat, K)
+    ref = po.fit(po.codes_to_r_matrix(codes), pat, K, dp, 1.0, 1.0, 0.1, 4, -np.inf, z0, p0)
+    for engine in (0, 1):
+        with Engine(codes, pat) as eng:
+            eng.set_engine(engine)
+            r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), max_iter=4, epsilon=-np.inf)
+            t = eng.timing()
+        if engine == 0 and K <= 64:
+            assert t["engine"] == 2, t  # these shapes must run on the fused kernel
+        assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+        assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
+        assert np.array_equal(r["pred_class"], ref["pred_class"])
