@@ -82,16 +82,35 @@ __global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, i
                              const int* __restrict__ ncat, ScanOut* out) {
   unsigned long long miss = 0;
   int mx = 0, bad = 0;
-  const int64_t total = n_rows * J;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total;
-       c += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = c / J;
-    const int j = (int)(c - i * J);
-    const uint8_t* rp = codes + i * row_bytes;
-    const int x = CB == 1 ? rp[j] : reinterpret_cast<const uint16_t*>(rp)[j];
-    miss += (x == 0);
-    mx = max(mx, x);
-    bad |= (x > ncat[j]);
+  // one 32-bit code word per thread and step; (row, word-in-row) advance incrementally so the
+  // loop has no 64-bit division
+  constexpr int FPW = 4 / CB;
+  const int WPR = row_bytes / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t srow = stride / WPR;
+  const int scol = (int)(stride - srow * WPR);
+  const int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t row = w0 / WPR;
+  int col = (int)(w0 - row * WPR);
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(codes);
+  while (row < n_rows) {
+    const uint32_t cw = words[row * WPR + col];
+#pragma unroll
+    for (int f = 0; f < FPW; f++) {
+      const int j = col * FPW + f;
+      if (j < J) {
+        const int x = CB == 1 ? (int)((cw >> (8 * f)) & 0xffu) : (int)((cw >> (16 * f)) & 0xffffu);
+        miss += (x == 0);
+        mx = max(mx, x);
+        bad |= (x > __ldg(ncat + j));
+      }
+    }
+    row += srow;
+    col += scol;
+    if (col >= WPR) {
+      col -= WPR;
+      row++;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     miss += __shfl_xor_sync(0xffffffffu, miss, o);
