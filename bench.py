@@ -322,7 +322,10 @@ def run_ours(args):
                         "+ result read-back + mixdir_b200_destroy, per step"},
         "gpu_launches": int(tm["total_launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                     "frac": achieved / peak,
+                     "traffic": (int(traffic["dram_bytes_per_row"] * N) if traffic and
+                                 tm["engine"] == 2 and J == 60 and K == 32 else None),
+                     "traffic_source": (traffic or {}).get("source"),
                      "kernel": "k_em_fused" if tm["engine"] == 2 else "k_em_generic",
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,

@@ -1,0 +1,47 @@
+"""Multi-GPU parity (skipped on boxes with one GPU): the single-process flavour
+(mixdir_b200_create with n_devices > 1: contiguous row shards, ncclCommInitAll, one grouped
+all-reduce of the statistics buffer per iteration) must reproduce the one-GPU fit."""
+import numpy as np
+import pytest
+
+from mixdir_b200 import Engine, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("dp", [False, True])
+def test_single_process_two_devices_match_one(dp):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    pat = np.array([16, 12, 8, 4, 2, 10] * 5, dtype=np.int32)
+    N, K = 50_001, 20
+    codes, _ = synth.make_codes(5, N, pat, K, p_na=0.05)
+    z0 = synth.zeta_init(5, N, K)
+    p0 = synth.phi_init(5, pat, K)
+    outs = []
+    for devs in (None, [0, 1]):
+        with Engine(codes, pat, devices=devs) as eng:
+            assert eng.n_missing == int((codes == 0).sum())
+            outs.append(eng.fit(K, z0.sum(axis=0), p0, dp=dp, max_iter=8, epsilon=-np.inf))
+    a, b = outs
+    assert np.max(np.abs(a["convergence"] - b["convergence"]) / np.abs(a["convergence"])) < 1e-12
+    assert np.array_equal(a["pred_class"], b["pred_class"])
+    assert np.max(np.abs(a["class_prob"] - b["class_prob"])) < 1e-10
+    np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-10, atol=1e-10)
+    # and against the oracle on a prefix small enough for the CPU
+    sub = slice(0, 2000)
+    ref = po.fit(po.codes_to_r_matrix(codes[sub]), pat, K, int(dp), 1.0, 1.0, 0.1, 5, -np.inf,
+                 synth.zeta_init(5, 2000, K), p0)
+    with Engine(codes[sub], pat, devices=[0, 1]) as eng:
+        r = eng.fit(K, synth.zeta_init(5, 2000, K).sum(axis=0), p0, dp=dp, max_iter=5, epsilon=-np.inf)
+        cp, pc = eng.predict(K, r["lambda_"], r["category_prob"])
+    assert np.max(np.abs(r["convergence"] - ref["convergence"]) / np.abs(ref["convergence"])) < 1e-9
+    assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < 1e-6
+    assert np.array_equal(r["pred_class"], ref["pred_class"])
+    assert np.max(np.abs(cp - r["class_prob"])) < 1e-12 and np.array_equal(pc, r["pred_class"])
