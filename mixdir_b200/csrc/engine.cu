@@ -20,6 +20,7 @@
 #include "../../include/mixdir_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "bucket.cuh"
 
 using namespace mxd;
 
@@ -564,7 +565,7 @@ extern "C" size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n
   return s * (size_t)n_latent;
 }
 extern "C" int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine) {
-  if (!h || engine < 0 || engine > 2) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (!h || engine < 0 || engine > 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
   h->engine_pref = engine;
   return MIXDIR_B200_OK;
 }
@@ -579,6 +580,7 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 // per warp (RG), warps (W) such that table + statistics slices fit shared memory
 // ---------------------------------------------------------------------------
 typedef void (*fused_fn)(FusedArgs);
+typedef void (*bucket_fn)(BucketArgs);
 
 static fused_fn pick_fused(int KC, int CB, int RG) {
 #define PICK(kc, cb, rg) \
@@ -592,86 +594,152 @@ static fused_fn pick_fused(int KC, int CB, int RG) {
   return nullptr;
 }
 
-static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+static bucket_fn pick_bucket(int KC, int CB, int RG) {
+#define PICK(kc, cb, rg) \
+  if (KC == kc && CB == cb && RG == rg) return k_em_bucket<kc, cb, rg>;
+  PICK(32, 1, 8) PICK(32, 1, 6) PICK(32, 1, 4) PICK(32, 1, 2)
+  PICK(16, 1, 8) PICK(16, 1, 6) PICK(16, 1, 4) PICK(16, 1, 2)
+  PICK(8, 1, 4) PICK(8, 1, 2)
+  PICK(32, 2, 8) PICK(32, 2, 6) PICK(32, 2, 4) PICK(32, 2, 2)
+  PICK(16, 2, 8) PICK(16, 2, 6) PICK(16, 2, 4) PICK(16, 2, 2)
+  PICK(8, 2, 4) PICK(8, 2, 2)
+#undef PICK
+  return nullptr;
+}
+
+static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
+  return p.engine == 3 ? (const void*)pick_bucket(p.KC, h->CB, p.RG)
+                       : (const void*)pick_fused(p.KC, h->CB, p.RG);
+}
+
+// how many clusters of this plan can be resident at once (0: cannot be scheduled)
+static int plan_occupancy(const mixdir_b200_handle* h, const Shard& s, const Plan& p) {
+  const void* fn = plan_fn(h, p);
+  if (!fn) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  int nclus = 0;
+  if (e == cudaSuccess) {
+    if (p.P > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(p.P * s.sm_count);
+      cfg.blockDim = dim3(32 * p.W);
+      cfg.dynamicSmemBytes = p.smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = p.P;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      e = cudaOccupancyMaxActiveClusters(&nclus, fn, &cfg);
+    } else {
+      int nb = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 32 * p.W, p.smem);
+      nclus = nb * s.sm_count;
+    }
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return nclus;
+}
+
+// engine 2: k_em_fused (row-owned M-step, read-modify-write per row and feature)
+static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
   Plan best;
   double best_cost = 1e300;
-  if (h->engine_pref != 1) {
-    const int kcs[3] = {32, 16, 8};
-    for (int KC : kcs) {
-      const int RPW = 32 / KC, FPW = 4 / h->CB;
-      if (RPW > FPW) continue;
-      const int P = (K + KC - 1) / KC;
-      if (P > 8) continue;
-      const int RG = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
-      const int W = std::min(16, h->WPR);
-      FusedSmem L(h->NR, KC, W, RG, h->WPR, FPW, P);
-      if (L.total > (size_t)s.smem_optin) continue;
-      // cost ~ shared-memory wavefronts per row: P CTAs x (1 / rows-per-instruction) x conflict factor
-      const double conflict = KC == 8 ? 1.5 : 1.0;
-      const double cost = P * conflict / RPW + 1e-3 * P;
-      if (cost < best_cost) {
-        best_cost = cost;
-        best.engine = 2;
-        best.KC = KC;
-        best.P = P;
-        best.RG = RG;
-        best.W = W;
-        best.KP = P * KC;
-        best.smem = L.total;
-        best.R = W * RG * RPW;
-      }
+  const int kcs[3] = {32, 16, 8};
+  for (int KC : kcs) {
+    const int RPW = 32 / KC, FPW = 4 / h->CB;
+    if (RPW > FPW) continue;
+    const int P = (K + KC - 1) / KC;
+    if (P > 8) continue;
+    const int RG = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
+    const int W = std::min(16, h->WPR);
+    FusedSmem L(h->NR, KC, W, RG, h->WPR, FPW, P);
+    if (L.total > (size_t)s.smem_optin) continue;
+    // cost ~ shared-memory wavefronts per row: P CTAs x (1 / rows-per-instruction) x conflict factor
+    const double conflict = KC == 8 ? 1.5 : 1.0;
+    const double cost = P * conflict / RPW + 1e-3 * P;
+    if (cost < best_cost) {
+      Plan c;
+      c.engine = 2; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
+      c.smem = L.total; c.R = W * RG * RPW;
+      c.n_clusters = plan_occupancy(h, s, c);
+      if (c.n_clusters < 1) continue;
+      best_cost = cost;
+      best = c;
     }
   }
-  if (best.engine == 2) {
-    fused_fn fn = pick_fused(best.KC, h->CB, best.RG);
-    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)best.smem);
-    int nclus = 0;
-    if (e == cudaSuccess) {
-      if (best.P > 1) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(best.P * s.sm_count);
-        cfg.blockDim = dim3(32 * best.W);
-        cfg.dynamicSmemBytes = best.smem;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = best.P;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        e = cudaOccupancyMaxActiveClusters(&nclus, (const void*)fn, &cfg);
-      } else {
-        int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)fn, 32 * best.W, best.smem);
-        nclus = nb * s.sm_count;
-      }
-    }
-    if (e != cudaSuccess || nclus < 1) {
-      cudaGetLastError();
-      if (h->engine_pref == 2)
-        return fail(MIXDIR_B200_CUDA_ERROR, std::string("fused kernel cannot be scheduled: ") +
-                                                cudaGetErrorString(e));
-      best = Plan();
-    } else {
-      best.n_clusters = nclus;
-    }
-  }
-  if (best.engine != 2) {
-    if (h->engine_pref == 2)
-      return fail(MIXDIR_B200_BAD_ARGUMENT, "fused kernel does not fit this problem shape (K, sum C_j)");
-    best = Plan();
-    best.engine = 1;
-    best.KP = (K + 7) & ~7;
-  }
+  if (best.engine != 2) return false;
   *out = best;
+  return true;
+}
+
+// engine 3: k_em_bucket (feature-owned M-step over code-sorted tiles)
+static bool plan_bucket(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+  Plan best;
+  double best_cost = 1e300;
+  int cmax = 0;
+  for (int c : h->ncat) cmax = std::max(cmax, c);
+  if (cmax > 4096) return false;  // bucket counters live in shared memory
+  const int entry = h->CB == 1 ? 2 : 4;
+  const int kcs[3] = {32, 16, 8};
+  const int rgs[4] = {8, 6, 4, 2};
+  for (int KC : kcs) {
+    const int RPW = 32 / KC, FPW = 4 / h->CB;
+    const int P = (K + KC - 1) / KC;
+    if (P > 8) continue;
+    const int W = 16;
+    for (int RG : rgs) {
+      const int R = W * RG * RPW;
+      if (RG * RPW > 32) continue;             // one owner lane per row
+      if (h->CB == 1 && R > 256) continue;     // 8-bit row index in the sort entries
+      if (!pick_bucket(KC, h->CB, RG)) continue;
+      BucketSmem L(h->NR, KC, W, RG, h->WPR, FPW, P, h->J, cmax, entry);
+      if (L.total > (size_t)s.smem_optin) continue;
+      const double conflict = KC == 8 ? 1.5 : 1.0;
+      const double cost = P * conflict / RPW + 1e-3 * P + 1e-4 * (8 - RG);
+      if (cost < best_cost) {
+        Plan c;
+        c.engine = 3; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
+        c.smem = L.total; c.R = R;
+        c.n_clusters = plan_occupancy(h, s, c);
+        if (c.n_clusters < 1) continue;
+        best_cost = cost;
+        best = c;
+      }
+      break;  // largest RG that fits for this KC
+    }
+  }
+  if (best.engine != 3) return false;
+  *out = best;
+  return true;
+}
+
+// engine_pref: 0 automatic (fused, else bucket, else generic), 1 generic, 2 fused, 3 bucket.
+// The bucket kernel moves fewer shared-memory bytes but executes twice the instructions and
+// measured slower (profiles/README.md), so it is only a fallback in automatic mode.
+static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+  const int pref = h->engine_pref;
+  if ((pref == 0 || pref == 2) && plan_fused(h, s, K, out)) return MIXDIR_B200_OK;
+  if (pref == 2)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "fused kernel does not fit this problem shape (K, sum C_j)");
+  if ((pref == 0 || pref == 3) && plan_bucket(h, s, K, out)) return MIXDIR_B200_OK;
+  if (pref == 3)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "bucket kernel does not fit this problem shape (K, sum C_j)");
+  Plan g;
+  g.engine = 1;
+  g.KP = (K + 7) & ~7;
+  *out = g;
   return MIXDIR_B200_OK;
 }
 
 static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, int max_iter) {
   CU_TRY(cudaSetDevice(s.device));
   const int KP = pl.KP;
-  const int nclus = pl.engine == 2 ? pl.n_clusters : 0;
+  const int nclus = pl.engine >= 2 ? pl.n_clusters : 0;
   const int nctas = nclus * pl.P;
   if (s.ws_K == K && s.ws_KP == KP && s.ws_iter >= max_iter && s.ws_clusters >= nclus &&
       s.ws_ctas >= nctas)
@@ -728,7 +796,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
   CU_TRY(cudaSetDevice(s.device));
   const size_t tab = (size_t)h->NR * pl.KP;
   CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
-  if (pl.engine == 2 && s.n_rows > 0) {
+  if (pl.engine >= 2 && s.n_rows > 0) {
     const int n_tiles = (int)((s.n_rows + pl.R - 1) / pl.R);
     const int nclus = std::min(pl.n_clusters, n_tiles);
     FusedArgs a;
@@ -747,7 +815,6 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
     a.cspart = s.d_cspart;
     a.Hpart = s.d_Hpart;
     a.underflow = s.d_underflow;
-    fused_fn fn = pick_fused(pl.KC, h->CB, pl.RG);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nclus * pl.P);
     cfg.blockDim = dim3(32 * pl.W);
@@ -761,7 +828,16 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
-    CU_TRY(cudaLaunchKernelEx(&cfg, fn, a));
+    if (pl.engine == 3) {
+      BucketArgs b;
+      b.f = a;
+      b.J = h->J;
+      b.ncat = s.d_ncat;
+      b.rowoff = s.d_rowoff;
+      CU_TRY(cudaLaunchKernelEx(&cfg, pick_bucket(pl.KC, h->CB, pl.RG), b));
+    } else {
+      CU_TRY(cudaLaunchKernelEx(&cfg, pick_fused(pl.KC, h->CB, pl.RG), a));
+    }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
     ReduceArgs r;
     r.NR = h->NR;
@@ -1046,7 +1122,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   if (!h || !log_prior || !table) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
-  if (engine < 0 || engine > 2) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (engine < 0 || engine > 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
   const int keep = h->engine_pref;
   if (engine) h->engine_pref = engine;
   Plan pl;
@@ -1073,7 +1149,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     double* d_zeta = nullptr;
     if (zeta && s.n_rows > 0) {
       RET_IF(dalloc(&d_zeta, (size_t)s.n_rows * K));
-      if (pl.engine == 2) {  // responsibilities come from the generic kernel (no scatter)
+      if (pl.engine >= 2) {  // responsibilities come from the generic kernel (no scatter)
         Plan g = pl;
         g.engine = 1;
         RET_IF(launch_em(h, s, K, g, d_zeta, false, nullptr, nullptr, &l));
