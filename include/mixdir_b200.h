@@ -85,7 +85,14 @@ size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n_latent);
  * n_devices/device_ids: single-process multi-GPU (what an R session needs: R is
  * one process).  Rows are split into contiguous blocks, one per device; each
  * iteration ends with one NCCL all-reduce of the statistics buffer.
- * n_devices = 0 or 1 with device_ids == NULL uses the current CUDA device. */
+ * n_devices = 0 or 1 with device_ids == NULL uses the current CUDA device.
+ *
+ * The upload is ASYNCHRONOUS: create returns once the chunked host-to-device copies are queued,
+ * and the first mixdir_b200_fit iteration consumes the chunks as they arrive (copy and compute
+ * overlap).  With pageable host memory the runtime stages the data before returning; with
+ * page-locked memory the caller must leave `codes` untouched until the first fit / predict /
+ * getter call on the handle has returned.  Code validity (code <= ncat[j]) is therefore
+ * reported by that first call (MIXDIR_B200_BAD_ARGUMENT), not by create. */
 int mixdir_b200_create(const void* codes, int code_bytes, int64_t n_rows, int n_features,
                        const int* ncat, int n_devices, const int* device_ids,
                        mixdir_b200_handle** out);

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(512, 1) k_em_bucket(BucketArgs ba) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
   const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
+  if (*a.bad) return;  // uniform over the grid: a code above C_j would index outside the tables
 
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(512, 1) k_em_bucket(BucketArgs ba) {
     double* Sp = a.Spart + (size_t)cluster_id * NR * KP;
     for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
       const int g = i / KC, c = i - g * KC;
-      Sp[(size_t)g * KP + rank * KC + c] = S_s[i];
+      double* dst = &Sp[(size_t)g * KP + rank * KC + c];
+      *dst = a.accumulate ? *dst + S_s[i] : S_s[i];
     }
 #pragma unroll
     for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);
@@ -352,12 +354,13 @@ __global__ void __launch_bounds__(512, 1) k_em_bucket(BucketArgs ba) {
     if (threadIdx.x < KC) {
       double s = 0;
       for (int w = 0; w < W; w++) s += red_s[w * KC + threadIdx.x];
-      a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x] = s;
+      double* dst = &a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x];
+      *dst = a.accumulate ? *dst + s : s;
     }
     if (threadIdx.x == 0) {
       double h = 0;
       for (int w = 0; w < W; w++) h += red_s[W * KC + w];
-      a.Hpart[blockIdx.x] = h;
+      a.Hpart[blockIdx.x] = a.accumulate ? a.Hpart[blockIdx.x] + h : h;
     }
     if (uflag) atomicExch(a.underflow, 1);
   }

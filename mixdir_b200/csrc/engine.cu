@@ -145,6 +145,18 @@ struct Shard {
   IterStatus* h_status = nullptr;  // pinned
   cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
   std::vector<cudaEvent_t> ev_em;
+  // asynchronous upload: chunks are copied on copy_stream, each followed by an event; the
+  // compute stream waits for (and scans) a chunk only when it first needs its rows
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> up_ev;
+  std::vector<int64_t> up_end;  // exclusive row end of chunk c
+  size_t up_seen = 0;           // chunks already waited for + scanned on the compute stream
+  ScanOut* d_scan = nullptr;    // NA count / largest code / validity, accumulated over chunks
+  double* d_stage[2] = {nullptr, nullptr};  // fp64 staging of create_from_r_matrix
+  // page-locked, device-mapped scratch for the small per-fit inputs: kernels pull them over
+  // PCIe themselves, so they do not queue behind the bulk upload on the H2D copy engine
+  unsigned char* h_pin = nullptr;
+  size_t h_pin_bytes = 0, h_pin_used = 0;
 };
 
 struct mixdir_b200_handle {
@@ -158,6 +170,7 @@ struct mixdir_b200_handle {
   std::vector<Shard> shards;
   int rank = 0, world = 1;   // multi-process flavour
   int engine_pref = 0;
+  bool scan_resolved = false;
   mixdir_b200_timing timing = {};
 };
 
@@ -204,11 +217,22 @@ static void free_workspace(Shard& s) {
 
 static void free_shard(Shard& s) {
   cudaSetDevice(s.device);
+  if (s.copy_stream) cudaStreamSynchronize(s.copy_stream);
+  if (s.stream) cudaStreamSynchronize(s.stream);
   free_workspace(s);
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
-  dfree(s.d_ragoff); dfree(s.d_na_row);
+  dfree(s.d_ragoff); dfree(s.d_na_row); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
+  if (s.copy_stream) {
+    cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
+    cudaStreamDestroy(s.copy_stream);
+  }
+  s.copy_stream = nullptr;
+  for (auto e : s.up_ev) cudaEventDestroy(e);
+  s.up_ev.clear();
   if (s.h_status) cudaFreeHost(s.h_status);
   s.h_status = nullptr;
+  if (s.h_pin) cudaFreeHost(s.h_pin);
+  s.h_pin = nullptr;
   for (auto e : s.ev_em) cudaEventDestroy(e);
   s.ev_em.clear();
   if (s.ev_loop0) cudaEventDestroy(s.ev_loop0);
@@ -263,6 +287,9 @@ static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   s.sm_count = prop.multiProcessorCount;
   s.smem_optin = (int)prop.sharedMemPerBlockOptin;
   CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+  RET_IF(dalloc(&s.d_scan, 1));
+  CU_TRY(cudaMemsetAsync(s.d_scan, 0, sizeof(ScanOut), s.stream));
   CU_TRY(cudaEventCreate(&s.ev_loop0));
   CU_TRY(cudaEventCreate(&s.ev_loop1));
   CU_TRY(cudaMallocHost((void**)&s.h_status, sizeof(IterStatus)));
@@ -281,36 +308,110 @@ static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   CU_TRY(cudaMemcpy(s.d_na_row, na.data(), h->NR, cudaMemcpyHostToDevice));
   const size_t bytes = (size_t)(s.n_rows + kRowPad) * h->row_bytes;
   RET_IF(dalloc(&s.d_codes, bytes));
-  CU_TRY(cudaMemsetAsync(s.d_codes, 0, bytes, s.stream));
+  // only the pad rows need zeroing; every real row is overwritten by the upload
+  CU_TRY(cudaMemsetAsync(s.d_codes + (size_t)s.n_rows * h->row_bytes, 0,
+                         (size_t)kRowPad * h->row_bytes, s.stream));
   return MIXDIR_B200_OK;
 }
 
-// scan the uploaded codes: NA count, largest code, validity
-static int scan_codes(mixdir_b200_handle* h) {
-  std::vector<ScanOut*> d_out(h->shards.size(), nullptr);
+// rows per upload chunk: ~8 chunks, multiples of 4096 rows (16-byte aligned tile starts)
+static int64_t upload_chunk_rows(int64_t n_rows) {
+  int64_t c = (n_rows + 7) / 8;
+  c = (c + 4095) / 4096 * 4096;
+  return std::max<int64_t>(c, 4096);
+}
+
+static int push_chunk_event(Shard& s, int64_t row_end) {
+  cudaEvent_t e;
+  CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU_TRY(cudaEventRecord(e, s.copy_stream));
+  s.up_ev.push_back(e);
+  s.up_end.push_back(row_end);
+  return MIXDIR_B200_OK;
+}
+
+// Asynchronous upload of packed codes: chunked copies on the copy stream.  Returns without
+// waiting; with page-locked source memory the copies overlap the first E+M pass.
+static int upload_codes(mixdir_b200_handle* h, Shard& s, const uint8_t* src_rows) {
+  if (s.n_rows == 0) return MIXDIR_B200_OK;
+  const size_t w = (size_t)h->J * h->CB;
+  const int64_t chunk = upload_chunk_rows(s.n_rows);
+  for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk) {
+    const int64_t nr = std::min(chunk, s.n_rows - r0);
+    uint8_t* dst = s.d_codes + (size_t)r0 * h->row_bytes;
+    const uint8_t* src = src_rows + (size_t)r0 * w;
+    if ((int)w == h->row_bytes)
+      CU_TRY(cudaMemcpyAsync(dst, src, w * nr, cudaMemcpyHostToDevice, s.copy_stream));
+    else
+      CU_TRY(cudaMemcpy2DAsync(dst, h->row_bytes, src, w, w, nr, cudaMemcpyHostToDevice,
+                               s.copy_stream));
+    RET_IF(push_chunk_event(s, r0 + nr));
+  }
+  return MIXDIR_B200_OK;
+}
+
+// Same for the reference's fp64 column-major matrix: copy a row block into one of two staging
+// buffers, pack it to codes on the copy stream, signal the chunk.
+static int upload_r_matrix(mixdir_b200_handle* h, Shard& s, const double* X, int64_t ld) {
+  if (s.n_rows == 0) return MIXDIR_B200_OK;
+  const int J = h->J;
+  const int64_t chunk = std::min<int64_t>(upload_chunk_rows(s.n_rows), 1 << 20);
+  RET_IF(dalloc(&s.d_stage[0], (size_t)chunk * J));
+  RET_IF(dalloc(&s.d_stage[1], (size_t)chunk * J));
+  int c = 0;
+  for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk, c++) {
+    const int64_t nr = std::min(chunk, s.n_rows - r0);
+    double* st = s.d_stage[c & 1];
+    CU_TRY(cudaMemcpy2DAsync(st, nr * sizeof(double), X + s.row0 + r0, ld * sizeof(double),
+                             nr * sizeof(double), J, cudaMemcpyHostToDevice, s.copy_stream));
+    uint8_t* dst = s.d_codes + (size_t)r0 * h->row_bytes;
+    const int grid = s.sm_count * 8;
+    if (h->CB == 1)
+      k_pack_r_matrix<1><<<grid, 256, 0, s.copy_stream>>>(st, nr, nr, J, dst, h->row_bytes, &s.d_scan->bad);
+    else
+      k_pack_r_matrix<2><<<grid, 256, 0, s.copy_stream>>>(st, nr, nr, J, dst, h->row_bytes, &s.d_scan->bad);
+    CU_TRY(cudaGetLastError());
+    RET_IF(push_chunk_event(s, r0 + nr));
+  }
+  return MIXDIR_B200_OK;
+}
+
+// make upload chunks [s.up_seen, upto] visible to the compute stream and scan them
+// (NA count, largest code = the reference's n_cat, validity)
+static int consume_upload(mixdir_b200_handle* h, Shard& s, size_t upto) {
+  CU_TRY(cudaSetDevice(s.device));
+  for (; s.up_seen <= upto && s.up_seen < s.up_ev.size(); s.up_seen++) {
+    const size_t c = s.up_seen;
+    CU_TRY(cudaStreamWaitEvent(s.stream, s.up_ev[c], 0));
+    const int64_t r0 = c == 0 ? 0 : s.up_end[c - 1];
+    const int64_t nr = s.up_end[c] - r0;
+    const uint8_t* base = s.d_codes + (size_t)r0 * h->row_bytes;
+    const int grid = (int)std::min<int64_t>(s.sm_count * 8, (nr * h->WPR + 255) / 256);
+    if (h->CB == 1)
+      k_scan_codes<1><<<grid, 256, 0, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan);
+    else
+      k_scan_codes<2><<<grid, 256, 0, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan);
+    CU_TRY(cudaGetLastError());
+  }
+  return MIXDIR_B200_OK;
+}
+
+// wait for the whole upload and bring NA count / largest code / validity to the host
+// (collective over ranks in the multi-process flavour)
+static int resolve_scan(mixdir_b200_handle* h) {
+  if (h->scan_resolved) return MIXDIR_B200_OK;
   int64_t miss = 0;
   int mx = 0, bad = 0;
-  for (size_t i = 0; i < h->shards.size(); i++) {
-    Shard& s = h->shards[i];
-    CU_TRY(cudaSetDevice(s.device));
-    RET_IF(dalloc(&d_out[i], 1));
-    CU_TRY(cudaMemsetAsync(d_out[i], 0, sizeof(ScanOut), s.stream));
-    if (s.n_rows > 0) {
-      const int grid = s.sm_count * 8;
-      if (h->CB == 1)
-        k_scan_codes<1><<<grid, 256, 0, s.stream>>>(s.d_codes, h->row_bytes, s.n_rows, h->J, s.d_ncat, d_out[i]);
-      else
-        k_scan_codes<2><<<grid, 256, 0, s.stream>>>(s.d_codes, h->row_bytes, s.n_rows, h->J, s.d_ncat, d_out[i]);
-      CU_TRY(cudaGetLastError());
-    }
+  for (auto& s : h->shards) {
+    if (!s.up_ev.empty()) RET_IF(consume_upload(h, s, s.up_ev.size() - 1));
   }
-  for (size_t i = 0; i < h->shards.size(); i++) {
-    Shard& s = h->shards[i];
+  for (auto& s : h->shards) {
     CU_TRY(cudaSetDevice(s.device));
     ScanOut o;
-    CU_TRY(cudaMemcpyAsync(&o, d_out[i], sizeof o, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaMemcpyAsync(&o, s.d_scan, sizeof o, cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
-    cudaFree(d_out[i]);
+    dfree(s.d_stage[0]);
+    dfree(s.d_stage[1]);
     miss += (int64_t)o.n_missing;
     mx = std::max(mx, o.max_code);
     bad |= o.bad;
@@ -331,20 +432,13 @@ static int scan_codes(mixdir_b200_handle* h) {
     mx = (int)v[1];
     bad = (int)v[2];
   }
-  if (bad) return fail(MIXDIR_B200_BAD_ARGUMENT, "a code exceeds its feature's number of categories");
   h->n_missing = miss;
   h->max_code = mx;
-  return MIXDIR_B200_OK;
-}
-
-static int upload_codes(mixdir_b200_handle* h, Shard& s, const uint8_t* src_rows) {
-  if (s.n_rows == 0) return MIXDIR_B200_OK;
-  const size_t w = (size_t)h->J * h->CB;
-  if ((int)w == h->row_bytes)
-    CU_TRY(cudaMemcpyAsync(s.d_codes, src_rows, w * s.n_rows, cudaMemcpyHostToDevice, s.stream));
-  else
-    CU_TRY(cudaMemcpy2DAsync(s.d_codes, h->row_bytes, src_rows, w, w, s.n_rows,
-                             cudaMemcpyHostToDevice, s.stream));
+  h->scan_resolved = true;
+  if (bad)
+    return fail(MIXDIR_B200_BAD_ARGUMENT,
+                "a code exceeds its feature's number of categories (or X holds a value that is "
+                "not a positive integer code or NA)");
   return MIXDIR_B200_OK;
 }
 
@@ -398,7 +492,6 @@ extern "C" int mixdir_b200_create(const void* codes, int code_bytes, int64_t n_r
     if (st == MIXDIR_B200_OK)
       st = upload_codes(h, s, (const uint8_t*)codes + (size_t)s.row0 * n_features * code_bytes);
   }
-  if (st == MIXDIR_B200_OK) st = scan_codes(h);
   if (st != MIXDIR_B200_OK) {
     std::string keep = g_err;
     mixdir_b200_destroy(h);
@@ -425,33 +518,9 @@ extern "C" int mixdir_b200_create_from_r_matrix(const double* X, int64_t n_rows,
   auto body = [&]() -> int {
     for (auto& s : h->shards) {
       RET_IF(init_shard_static(h, s));
-      // stream the fp64 column-major matrix through a staging buffer, pack on device
-      const int64_t chunk = std::min<int64_t>(std::max<int64_t>(s.n_rows, 1), 1 << 20);
-      double* d_x = nullptr;
-      int* d_bad = nullptr;
-      RET_IF(dalloc(&d_x, (size_t)chunk * n_features));
-      RET_IF(dalloc(&d_bad, 1));
-      CU_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), s.stream));
-      for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk) {
-        const int64_t nr = std::min(chunk, s.n_rows - r0);
-        CU_TRY(cudaMemcpy2DAsync(d_x, nr * sizeof(double), X + s.row0 + r0, n_rows * sizeof(double),
-                                 nr * sizeof(double), n_features, cudaMemcpyHostToDevice, s.stream));
-        uint8_t* dst = s.d_codes + (size_t)r0 * h->row_bytes;
-        const int grid = s.sm_count * 8;
-        if (cb == 1)
-          k_pack_r_matrix<1><<<grid, 256, 0, s.stream>>>(d_x, nr, nr, n_features, dst, h->row_bytes, d_bad);
-        else
-          k_pack_r_matrix<2><<<grid, 256, 0, s.stream>>>(d_x, nr, nr, n_features, dst, h->row_bytes, d_bad);
-        CU_TRY(cudaGetLastError());
-      }
-      int bad = 0;
-      CU_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-      CU_TRY(cudaStreamSynchronize(s.stream));
-      cudaFree(d_x);
-      cudaFree(d_bad);
-      if (bad) return fail(MIXDIR_B200_BAD_ARGUMENT, "X holds a value that is not a positive integer code or NA");
+      RET_IF(upload_r_matrix(h, s, X, n_rows));
     }
-    return scan_codes(h);
+    return MIXDIR_B200_OK;
   };
   if (st == MIXDIR_B200_OK) st = body();
   if (st != MIXDIR_B200_OK) {
@@ -540,8 +609,7 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
     s.comm = comm->comm;
     s.owns_comm = false;
     RET_IF(init_shard_static(h, s));
-    RET_IF(upload_codes(h, s, (const uint8_t*)codes_local));
-    return scan_codes(h);
+    return upload_codes(h, s, (const uint8_t*)codes_local);
   };
   if (st == MIXDIR_B200_OK) st = body();
   if (st != MIXDIR_B200_OK) {
@@ -555,8 +623,14 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
 }
 
 extern "C" int64_t mixdir_b200_n_rows(const mixdir_b200_handle* h) { return h ? h->n_rows : -1; }
-extern "C" int mixdir_b200_max_code(const mixdir_b200_handle* h) { return h ? h->max_code : -1; }
-extern "C" int64_t mixdir_b200_n_missing(const mixdir_b200_handle* h) { return h ? h->n_missing : -1; }
+extern "C" int mixdir_b200_max_code(const mixdir_b200_handle* h) {
+  if (!h || resolve_scan(const_cast<mixdir_b200_handle*>(h)) != MIXDIR_B200_OK) return -1;
+  return h->max_code;
+}
+extern "C" int64_t mixdir_b200_n_missing(const mixdir_b200_handle* h) {
+  if (!h || resolve_scan(const_cast<mixdir_b200_handle*>(h)) != MIXDIR_B200_OK) return -1;
+  return h->n_missing;
+}
 extern "C" const char* mixdir_b200_last_error(void) { return g_err.c_str(); }
 extern "C" int mixdir_b200_abi_version(void) { return MIXDIR_B200_ABI_VERSION; }
 extern "C" size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n_latent) {
@@ -750,7 +824,7 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   RET_IF(dalloc(&s.d_T, tab));
   RET_IF(dalloc(&s.d_phi, tab));
   RET_IF(dalloc(&s.d_logU, tab));
-  RET_IF(dalloc(&s.d_stats, tab + KP + 2));
+  RET_IF(dalloc(&s.d_stats, tab + KP + 4));
   RET_IF(dalloc(&s.d_logprior, KP));
   RET_IF(dalloc(&s.d_cs_a, kMaxClasses));
   RET_IF(dalloc(&s.d_cs_b, kMaxClasses));
@@ -782,109 +856,192 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   return MIXDIR_B200_OK;
 }
 
-static int upload_ragoff(mixdir_b200_handle* h, Shard& s, int K) {
-  std::vector<int64_t> ro(h->J);
-  for (int j = 0; j < h->J; j++) ro[j] = h->ragoff1[j] * K;
-  CU_TRY(cudaMemcpyAsync(s.d_ragoff, ro.data(), h->J * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
-  CU_TRY(cudaStreamSynchronize(s.stream));  // ro is a stack temporary
+__global__ void k_copy_words(uint64_t* __restrict__ dst, const uint64_t* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+// start a new batch of staged inputs (the compute stream is idle between API calls)
+static int pin_reset(Shard& s, size_t need) {
+  CU_TRY(cudaSetDevice(s.device));
+  if (s.h_pin_bytes < need) {
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    if (s.h_pin) cudaFreeHost(s.h_pin);
+    s.h_pin = nullptr;
+    s.h_pin_bytes = 0;
+    CU_TRY(cudaHostAlloc((void**)&s.h_pin, need, cudaHostAllocMapped | cudaHostAllocPortable));
+    s.h_pin_bytes = need;
+  }
+  s.h_pin_used = 0;
   return MIXDIR_B200_OK;
 }
 
-// one E+M pass on a shard: statistics land in s.d_stats (local, before any all-reduce)
+// host array -> device array through the mapped scratch (bytes must be a multiple of 8)
+static int pin_send(Shard& s, void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes == 0) return MIXDIR_B200_OK;
+  if (s.h_pin_used + bytes > s.h_pin_bytes) return fail(MIXDIR_B200_CUDA_ERROR, "staging buffer overflow");
+  unsigned char* p = s.h_pin + s.h_pin_used;
+  memcpy(p, src_host, bytes);
+  s.h_pin_used += (bytes + 63) & ~(size_t)63;
+  void* dp = nullptr;
+  CU_TRY(cudaHostGetDevicePointer(&dp, p, 0));
+  const size_t n = bytes / 8;
+  const int grid = (int)std::min<size_t>((n + 255) / 256, 64);
+  k_copy_words<<<grid, 256, 0, s.stream>>>((uint64_t*)dst_dev, (const uint64_t*)dp, n);
+  CU_TRY(cudaGetLastError());
+  return MIXDIR_B200_OK;
+}
+
+static int upload_ragoff(mixdir_b200_handle* h, Shard& s, int K) {
+  std::vector<int64_t> ro(h->J);
+  for (int j = 0; j < h->J; j++) ro[j] = h->ragoff1[j] * K;
+  return pin_send(s, s.d_ragoff, ro.data(), h->J * sizeof(int64_t));
+}
+
+// One E+M pass on a shard: statistics land in s.d_stats (local, before any all-reduce).
+// While an asynchronous upload is still in flight the pass runs CHUNKED: the compute stream
+// waits for upload chunk c (and scans it), then launches the kernel on the rows that are
+// complete so far, so the first iteration overlaps the host-to-device copy.
 static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, double* zeta_out,
                      bool scatter, cudaEvent_t ev0, cudaEvent_t ev1, int* launches) {
   CU_TRY(cudaSetDevice(s.device));
   const size_t tab = (size_t)h->NR * pl.KP;
   CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
+  // row ranges of this pass: one per pending upload chunk, else the whole shard
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  std::vector<size_t> range_chunk;  // upload chunk to consume before range i (or SIZE_MAX)
+  const int64_t align = pl.engine >= 2 ? pl.R : 1;
+  if (s.up_seen < s.up_ev.size()) {
+    int64_t prev = 0;
+    for (size_t c = 0; c < s.up_ev.size(); c++) {
+      const bool last = c + 1 == s.up_ev.size();
+      const int64_t end = last ? s.n_rows : (s.up_end[c] / align) * align;
+      if (c < s.up_seen && !last) continue;  // (cannot happen today; keeps the logic general)
+      if (end > prev || last) {
+        ranges.push_back({prev, std::max(end, prev)});
+        range_chunk.push_back(c);
+        prev = std::max(end, prev);
+      }
+    }
+  } else {
+    ranges.push_back({0, s.n_rows});
+    range_chunk.push_back(SIZE_MAX);
+  }
+  const bool chunked = ranges.size() > 1;
+
   if (pl.engine >= 2 && s.n_rows > 0) {
-    const int n_tiles = (int)((s.n_rows + pl.R - 1) / pl.R);
-    const int nclus = std::min(pl.n_clusters, n_tiles);
-    FusedArgs a;
-    a.codes = reinterpret_cast<const uint32_t*>(s.d_codes);
-    a.n_rows = s.n_rows;
-    a.n_tiles = n_tiles;
-    a.WPR = h->WPR;
-    a.NR = h->NR;
-    a.K = K;
-    a.KP = pl.KP;
-    a.P = pl.P;
-    a.rowoff_pad = s.d_rowoff_pad;
-    a.T = s.d_T;
-    a.logprior = s.d_logprior;
-    a.Spart = s.d_Spart;
-    a.cspart = s.d_cspart;
-    a.Hpart = s.d_Hpart;
-    a.underflow = s.d_underflow;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nclus * pl.P);
-    cfg.blockDim = dim3(32 * pl.W);
-    cfg.dynamicSmemBytes = pl.smem;
-    cfg.stream = s.stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = pl.P;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    if (chunked) {  // partial buffers accumulate over the launches
+      CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab * sizeof(double), s.stream));
+      CU_TRY(cudaMemsetAsync(s.d_cspart, 0, (size_t)pl.n_clusters * pl.KP * sizeof(double), s.stream));
+      CU_TRY(cudaMemsetAsync(s.d_Hpart, 0, (size_t)pl.n_clusters * pl.P * sizeof(double), s.stream));
+    }
     if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
-    if (pl.engine == 3) {
-      BucketArgs b;
-      b.f = a;
-      b.J = h->J;
-      b.ncat = s.d_ncat;
-      b.rowoff = s.d_rowoff;
-      CU_TRY(cudaLaunchKernelEx(&cfg, pick_bucket(pl.KC, h->CB, pl.RG), b));
-    } else {
-      CU_TRY(cudaLaunchKernelEx(&cfg, pick_fused(pl.KC, h->CB, pl.RG), a));
+    int max_clus = 0;
+    for (size_t i = 0; i < ranges.size(); i++) {
+      if (range_chunk[i] != SIZE_MAX) RET_IF(consume_upload(h, s, range_chunk[i]));
+      const int64_t r0 = ranges[i].first, nr = ranges[i].second - ranges[i].first;
+      if (nr <= 0) continue;
+      const int n_tiles = (int)((nr + pl.R - 1) / pl.R);
+      const int nclus = std::min(pl.n_clusters, n_tiles);
+      max_clus = std::max(max_clus, nclus);
+      FusedArgs a;
+      a.codes = reinterpret_cast<const uint32_t*>(s.d_codes + (size_t)r0 * h->row_bytes);
+      a.n_rows = nr;
+      a.n_tiles = n_tiles;
+      a.WPR = h->WPR;
+      a.NR = h->NR;
+      a.K = K;
+      a.KP = pl.KP;
+      a.P = pl.P;
+      a.rowoff_pad = s.d_rowoff_pad;
+      a.T = s.d_T;
+      a.logprior = s.d_logprior;
+      a.Spart = s.d_Spart;
+      a.cspart = s.d_cspart;
+      a.Hpart = s.d_Hpart;
+      a.underflow = s.d_underflow;
+      a.accumulate = chunked ? 1 : 0;
+      a.bad = &s.d_scan->bad;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nclus * pl.P);
+      cfg.blockDim = dim3(32 * pl.W);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = s.stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = pl.P;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (pl.engine == 3) {
+        BucketArgs b;
+        b.f = a;
+        b.J = h->J;
+        b.ncat = s.d_ncat;
+        b.rowoff = s.d_rowoff;
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_bucket(pl.KC, h->CB, pl.RG), b));
+      } else {
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_fused(pl.KC, h->CB, pl.RG), a));
+      }
+      *launches += 1;
     }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
     ReduceArgs r;
     r.NR = h->NR;
     r.KP = pl.KP;
-    r.n_clusters = nclus;
-    r.n_ctas = nclus * pl.P;
+    r.n_clusters = chunked ? pl.n_clusters : max_clus;
+    r.n_ctas = r.n_clusters * pl.P;
     r.Spart = s.d_Spart;
     r.cspart = s.d_cspart;
     r.Hpart = s.d_Hpart;
     r.underflow = s.d_underflow;
+    r.scan = s.d_scan;
     r.na_row = s.d_na_row;
     r.stats = s.d_stats;
     const int rgrid = (int)std::min<size_t>((tab + 255) / 256, (size_t)s.sm_count * 4);
     k_reduce_partials<<<rgrid, 256, 0, s.stream>>>(r);
     CU_TRY(cudaGetLastError());
-    *launches += 2;
-    h->timing.grid_ctas = nclus * pl.P;
+    *launches += 1;
+    h->timing.grid_ctas = max_clus * pl.P;
   } else {
-    CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 2) * sizeof(double), s.stream));
-    GenericArgs g;
-    g.codes = s.d_codes;
-    g.row_bytes = h->row_bytes;
-    g.n_rows = s.n_rows;
-    g.J = h->J;
-    g.K = K;
-    g.KP = pl.KP;
-    g.rowoff = s.d_rowoff;
-    g.T = s.d_T;
-    g.logprior = s.d_logprior;
-    g.stats = s.d_stats;
-    g.NR = h->NR;
-    g.underflow = s.d_underflow;
-    g.zeta_out = zeta_out;
-    g.do_scatter = scatter ? 1 : 0;
-    const int grid = s.sm_count * 8;
+    CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
     if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
-    if (s.n_rows > 0) {
+    for (size_t i = 0; i < ranges.size(); i++) {
+      if (range_chunk[i] != SIZE_MAX) RET_IF(consume_upload(h, s, range_chunk[i]));
+      const int64_t r0 = ranges[i].first, nr = ranges[i].second - ranges[i].first;
+      if (nr <= 0) continue;
+      GenericArgs g;
+      g.codes = s.d_codes + (size_t)r0 * h->row_bytes;
+      g.row_bytes = h->row_bytes;
+      g.n_rows = nr;
+      g.J = h->J;
+      g.K = K;
+      g.KP = pl.KP;
+      g.rowoff = s.d_rowoff;
+      g.T = s.d_T;
+      g.logprior = s.d_logprior;
+      g.stats = s.d_stats;
+      g.NR = h->NR;
+      g.underflow = s.d_underflow;
+      g.zeta_out = zeta_out;
+      g.zeta_ld = s.n_rows;
+      g.zeta_row0 = r0;
+      g.do_scatter = scatter ? 1 : 0;
+      g.bad = &s.d_scan->bad;
+      const int grid = s.sm_count * 8;
       if (h->CB == 1)
         k_em_generic<1><<<grid, 256, 0, s.stream>>>(g);
       else
         k_em_generic<2><<<grid, 256, 0, s.stream>>>(g);
       CU_TRY(cudaGetLastError());
+      *launches += 1;
     }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
-    k_flag_to_stats<<<1, 1, 0, s.stream>>>(s.d_underflow, s.d_stats + tab + pl.KP + 1);
+    k_tail_to_stats<<<1, 1, 0, s.stream>>>(s.d_underflow, s.d_scan, s.d_stats + tab + pl.KP + 1);
     CU_TRY(cudaGetLastError());
-    *launches += 2;
+    *launches += 1;
   }
   return MIXDIR_B200_OK;
 }
@@ -911,6 +1068,9 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   RET_IF(check_fit_args(h, p));
   if (!colsum_init || !phi_init) return fail(MIXDIR_B200_BAD_ARGUMENT, "colsum_init / phi_init is NULL");
   const int K = p->n_latent, J = h->J;
+  // the table needs n_cat = max(X) (R/mixdir_vi.R:8) before the first pass: when the caller
+  // does not pass it, wait for the upload scan (no upload/compute overlap in that case)
+  if (p->n_cat_bound <= 0) RET_IF(resolve_scan(h));
   const int n_cat_bound = p->n_cat_bound > 0 ? p->n_cat_bound : h->max_code;
   Plan pl;
   RET_IF(plan_engine(h, h->shards[0], K, &pl));
@@ -926,14 +1086,15 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   // ---- initial state on every shard: class masses + table from phi_init ----
   for (auto& s : h->shards) {
     RET_IF(ensure_workspace(h, s, K, pl, p->max_iter));
+    RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096));
     RET_IF(upload_ragoff(h, s, K));
     while ((int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreate(&e));
       s.ev_em.push_back(e);
     }
-    CU_TRY(cudaMemcpyAsync(s.d_cs_a, colsum_init, K * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CU_TRY(cudaMemcpyAsync(s.d_rag_a, phi_init, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    RET_IF(pin_send(s, s.d_cs_a, colsum_init, K * sizeof(double)));
+    RET_IF(pin_send(s, s.d_rag_a, phi_init, rag * sizeof(double)));
     CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
     CU_TRY(cudaMemsetAsync(s.d_warn, 0, sizeof(int), s.stream));
     ScatterRagArgs ra = {J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_phi, 0, 0.0};
@@ -964,17 +1125,17 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
       if (si == 0) launches += 1 + l;
       stat_bufs[si] = s.d_stats;
     }
-    RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 2, nccl::kDouble, nccl::kSum));
+    RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
     for (size_t si = 0; si < h->shards.size(); si++) {
       Shard& s = h->shards[si];
       CU_TRY(cudaSetDevice(s.device));
       ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
                       s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
       k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
-      FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, (double)K * (double)h->n_missing,
-                         s.d_pieces, s.d_stats + tab, s.d_stats + tab + pl.KP,
-                         s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior, s.d_cs_b, s.d_trace,
-                         s.d_status};
+      FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, s.d_stats + tab + pl.KP + 2,
+                         s.d_stats + tab + pl.KP + 3, s.d_pieces, s.d_stats + tab,
+                         s.d_stats + tab + pl.KP, s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior,
+                         s.d_cs_b, s.d_trace, s.d_status};
       k_finalize<<<1, 256, 0, s.stream>>>(fa);
       CU_TRY(cudaGetLastError());
       std::swap(s.d_cs_a, s.d_cs_b);
@@ -991,6 +1152,10 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
       last_elbo = s0.h_status->elbo;
       warn = s0.h_status->warn;
       conv = s0.h_status->converged;
+      if (s0.h_status->bad) {  // the upload scan found an invalid code: nothing was computed
+        status = MIXDIR_B200_BAD_ARGUMENT;
+        break;
+      }
       if (s0.h_status->underflow) {
         status = MIXDIR_B200_UNDERFLOW;
         break;
@@ -1026,10 +1191,16 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   if (n_iter) *n_iter = iters;
   if (converged) *converged = conv;
   if (elbo) *elbo = last_elbo;
+  if (status == MIXDIR_B200_BAD_ARGUMENT) {
+    if (warn_flags) *warn_flags = 0;
+    return fail(status, "a code exceeds its feature's number of categories (or X holds a value "
+                        "that is not a positive integer code or NA)");
+  }
   if (status != MIXDIR_B200_OK) {
     if (warn_flags) *warn_flags = warn;
     return fail(status, "zeta underflow: some row has rowSums(zeta) == 0");
   }
+  RET_IF(resolve_scan(h));  // upload complete by now; validates the codes when max_iter == 0
 
   // ---- results (R/mixdir_vi.R:119-155) ----
   for (size_t si = 0; si < h->shards.size(); si++) {
@@ -1096,6 +1267,7 @@ extern "C" int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const do
   if (!h || !lambda || !category_prob) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  RET_IF(resolve_scan(h));
   Plan pl;
   pl.engine = 1;
   pl.KP = (K + 7) & ~7;
@@ -1105,6 +1277,7 @@ extern "C" int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const do
   for (int k = 0; k < K; k++) lpad[k] = lambda[k];
   for (auto& s : h->shards) {
     RET_IF(ensure_workspace(h, s, K, pl, 1));
+    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096));
     RET_IF(upload_ragoff(h, s, K));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, category_prob, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_lambda_pad, lpad.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
@@ -1123,6 +1296,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
   if (engine < 0 || engine > 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  RET_IF(resolve_scan(h));
   const int keep = h->engine_pref;
   if (engine) h->engine_pref = engine;
   Plan pl;
@@ -1138,6 +1312,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   for (size_t si = 0; si < h->shards.size(); si++) {
     Shard& s = h->shards[si];
     RET_IF(ensure_workspace(h, s, K, pl, 1));
+    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096));
     RET_IF(upload_ragoff(h, s, K));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
@@ -1165,7 +1340,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     }
     bufs[si] = s.d_stats;
   }
-  RET_IF(allreduce(h, bufs, tab + pl.KP + 2, nccl::kDouble, nccl::kSum));
+  RET_IF(allreduce(h, bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
   {
     Shard& s = h->shards[0];
     CU_TRY(cudaSetDevice(s.device));

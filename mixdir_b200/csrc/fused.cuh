@@ -48,6 +48,8 @@ struct FusedArgs {
   double* cspart;
   double* Hpart;
   int* underflow;
+  int accumulate;         // 1: add to the partial buffers (chunked first iteration), 0: overwrite
+  const int* bad;         // invalid codes seen by the upload scan: do nothing
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
   const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
+  if (*a.bad) return;  // uniform over the grid: a code above C_j would index outside the tables
 
   // ---- prologue: barriers, first tile in flight, tables into shared memory ----
   if (threadIdx.x == 0) {
@@ -379,7 +382,8 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
     double* Sp = a.Spart + (size_t)cluster_id * NR * KP;
     for (int i = threadIdx.x; i < NR * KC; i += blockDim.x) {
       const int g = i / KC, c = i - g * KC;
-      Sp[(size_t)g * KP + rank * KC + c] = S_s[i];
+      double* dst = &Sp[(size_t)g * KP + rank * KC + c];
+      *dst = a.accumulate ? *dst + S_s[i] : S_s[i];
     }
 #pragma unroll
     for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);
@@ -390,12 +394,13 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
     if (threadIdx.x < KC) {
       double s = 0;
       for (int w = 0; w < W; w++) s += red_s[w * KC + threadIdx.x];
-      a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x] = s;
+      double* dst = &a.cspart[(size_t)cluster_id * KP + rank * KC + threadIdx.x];
+      *dst = a.accumulate ? *dst + s : s;
     }
     if (threadIdx.x == 0) {
       double h = 0;
       for (int w = 0; w < W; w++) h += red_s[W * KC + w];
-      a.Hpart[blockIdx.x] = h;
+      a.Hpart[blockIdx.x] = a.accumulate ? a.Hpart[blockIdx.x] + h : h;
     }
     if (uflag) atomicExch(a.underflow, 1);
   }

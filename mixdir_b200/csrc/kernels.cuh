@@ -339,12 +339,15 @@ struct IterStatus {
   int warn;
   int underflow;
   int iter;  // 0-based index of the iteration just finished
+  int bad;   // some code exceeded its feature's number of categories (any rank)
+  int pad_;
 };
 
 struct FinalizeArgs {
   int J, K, KP, dp, iter;
   double epsilon;
-  double k_times_nmissing;  // K * nNA: the "+1 per NA cell per class" of mixdir_impl.cpp:29-30
+  const double* n_missing;  // nNA (all ranks): "+1 per NA cell per class", mixdir_impl.cpp:29-30
+  const double* bad;        // > 0 if any rank saw an invalid code
   const double* pieces;     // [J*K][3]
   const double* cs;         // [KP] new class masses (unpermuted)
   const double* H;          // entropy sum (R/mixdir_vi.R:181-184)
@@ -358,6 +361,7 @@ struct FinalizeArgs {
 
 __global__ void k_finalize(FinalizeArgs a) {
   __shared__ double red[3][256];
+  const int K = a.K;
   const int n = a.J * a.K;
   double s0 = 0, s1 = 0, s2 = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -378,8 +382,7 @@ __global__ void k_finalize(FinalizeArgs a) {
     __syncthreads();
   }
   if (threadIdx.x != 0) return;
-  const int K = a.K;
-  const double tC = red[0][0], tD = red[1][0] + a.k_times_nmissing, tG = red[2][0];
+  const double tC = red[0][0], tD = red[1][0] + (double)K * (*a.n_missing), tG = red[2][0];
   double tB = 0;
   if (!a.dp) {
     for (int k = 0; k < K; k++) {
@@ -409,6 +412,7 @@ __global__ void k_finalize(FinalizeArgs a) {
   s->converged = conv;
   s->warn = warn;
   s->underflow = (*a.underflow > 0.0) ? 1 : 0;
+  s->bad = (*a.bad > 0.0) ? 1 : 0;
   s->iter = a.iter;
 }
 
@@ -515,7 +519,7 @@ __global__ void k_table_to_ragged(ScatterRagArgs a, double* out) {
 }
 
 // ---------------------------------------------------------------------------
-// statistics buffer:  [ S : NR*KP | cs : KP | H | underflow ]   (doubles)
+// statistics buffer:  [ S : NR*KP | cs : KP | H | underflow | nNA | bad ]   (doubles)
 // ---------------------------------------------------------------------------
 
 // deterministic reduction of the per-cluster partials of the fused kernel
@@ -526,6 +530,7 @@ struct ReduceArgs {
   const double* cspart;  // [n_clusters][KP]
   const double* Hpart;   // [n_ctas]
   const int* underflow;  // device flag
+  const ScanOut* scan;   // NA count / validity of this rank's codes
   const uint8_t* na_row; // [NR] 1 for NA rows (their S entries are scratch)
   double* stats;
 };
@@ -549,12 +554,17 @@ __global__ void k_reduce_partials(ReduceArgs a) {
       for (int c = 0; c < a.n_ctas; c++) h += a.Hpart[c];
       a.stats[n + a.KP] = h;
       a.stats[n + a.KP + 1] = (*a.underflow) ? 1.0 : 0.0;
+      a.stats[n + a.KP + 2] = (double)a.scan->n_missing;
+      a.stats[n + a.KP + 3] = a.scan->bad ? 1.0 : 0.0;
     }
   }
 }
 
-__global__ void k_flag_to_stats(const int* underflow, double* slot) {
-  *slot = (*underflow) ? 1.0 : 0.0;
+// tail of the statistics buffer for the generic kernel: [underflow | nNA | bad]
+__global__ void k_tail_to_stats(const int* underflow, const ScanOut* scan, double* slot) {
+  slot[0] = (*underflow) ? 1.0 : 0.0;
+  slot[1] = (double)scan->n_missing;
+  slot[2] = scan->bad ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -575,7 +585,10 @@ struct GenericArgs {
   int NR;
   int* underflow;
   double* zeta_out;        // nullable; n_rows x K column-major
+  int64_t zeta_ld;         // leading dimension (rows) of zeta_out
+  int64_t zeta_row0;       // row offset of this launch inside zeta_out
   int do_scatter;
+  const int* bad;          // invalid codes seen by the upload scan: do nothing
 };
 
 template <int CB>
@@ -585,6 +598,7 @@ __global__ void __launch_bounds__(256) k_em_generic(GenericArgs a) {
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int K = a.K, KP = a.KP;
   const int cpl = (K + 31) >> 5;
+  if (*a.bad) return;  // a code above C_j would index outside the tables
   double csacc[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) csacc[c] = 0;
@@ -635,7 +649,7 @@ __global__ void __launch_bounds__(256) k_em_generic(GenericArgs a) {
         e[c] = z;
         csacc[c] += z;
         hacc -= (z > DBL_MIN) ? z * ((l[c] - m) - logs) : kTiny;  // entrop_zeta, R/mixdir_vi.R:181
-        if (a.zeta_out) a.zeta_out[row + (int64_t)k * a.n_rows] = z;
+        if (a.zeta_out) a.zeta_out[a.zeta_row0 + row + (int64_t)k * a.zeta_ld] = z;
       }
     }
     if (a.do_scatter) {

@@ -138,11 +138,18 @@ class Engine:
 
     @property
     def max_code(self):
-        return _capi.lib().mixdir_b200_max_code(self._h)
+        """largest code present = the reference's n_cat (waits for the asynchronous upload)"""
+        v = _capi.lib().mixdir_b200_max_code(self._h)
+        if v < 0:
+            raise MixdirError(_capi.BAD_ARGUMENT, f"mixdir_b200: {_capi.last_error()}")
+        return v
 
     @property
     def n_missing(self):
-        return _capi.lib().mixdir_b200_n_missing(self._h)
+        v = _capi.lib().mixdir_b200_n_missing(self._h)
+        if v < 0:
+            raise MixdirError(_capi.BAD_ARGUMENT, f"mixdir_b200: {_capi.last_error()}")
+        return v
 
     def set_engine(self, engine: int):
         _check(_capi.lib().mixdir_b200_set_engine(self._h, engine))

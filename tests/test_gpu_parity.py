@@ -207,8 +207,16 @@ def test_create_from_r_matrix_and_u16():
 
 def test_bad_arguments():
     codes = np.array([[1, 2], [3, 1]], dtype=np.uint8)
-    with pytest.raises(MixdirError, match="exceeds"):
-        Engine(codes, [2, 2])  # code 3 > C_0 = 2
+    # code 3 > C_0 = 2: the upload is asynchronous, the first call that needs the data reports it
+    with Engine(codes, [2, 2]) as eng:
+        with pytest.raises(MixdirError, match="exceeds"):
+            eng.max_code
+    with Engine(codes, [2, 2]) as eng:
+        with pytest.raises(MixdirError, match="exceeds"):
+            eng.fit(2, [1.0, 1.0], np.ones(8), max_iter=3, n_cat_bound=2)
+    with Engine.from_r_matrix(np.array([[1.0, 2.5], [np.nan, 1.0]]), [2, 3]) as eng:
+        with pytest.raises(MixdirError, match="not a positive integer"):
+            eng.n_missing
     with Engine(codes, [3, 2]) as eng:
         with pytest.raises(ValueError):
             eng.fit(2, [1.0, 1.0], np.ones(3))  # wrong phi_init length (R/mixdir_vi.R:41-47)
