@@ -121,6 +121,11 @@ int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_r
 
 int mixdir_b200_destroy(mixdir_b200_handle* h);
 
+/* Device and page-locked buffers of destroyed handles are kept in a process-wide cache and reused
+ * by later handles of the same shapes (allocation and page-locking cost milliseconds).  This
+ * call returns all cached blocks to the driver. */
+int mixdir_b200_release_cache(void);
+
 /* rows held by this handle (local shard rows in the multi-process flavour) */
 int64_t mixdir_b200_n_rows(const mixdir_b200_handle* h);
 /* largest code present = the reference's n_cat (R/mixdir_vi.R:8); global over ranks */

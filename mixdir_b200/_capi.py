@@ -19,7 +19,7 @@ WARN_ELBO_DECREASED, WARN_DP_LAST_COMPONENT = 1, 2
 SYMBOLS = [
     "mixdir_b200_ragged_size", "mixdir_b200_create", "mixdir_b200_create_from_r_matrix",
     "mixdir_b200_nccl_unique_id", "mixdir_b200_comm_init", "mixdir_b200_comm_destroy",
-    "mixdir_b200_create_dist", "mixdir_b200_destroy",
+    "mixdir_b200_create_dist", "mixdir_b200_destroy", "mixdir_b200_release_cache",
     "mixdir_b200_n_rows", "mixdir_b200_max_code", "mixdir_b200_n_missing", "mixdir_b200_fit",
     "mixdir_b200_predict", "mixdir_b200_estep", "mixdir_b200_last_timing",
     "mixdir_b200_set_engine", "mixdir_b200_last_error", "mixdir_b200_abi_version",

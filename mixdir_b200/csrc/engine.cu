@@ -14,13 +14,17 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mixdir_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "bucket.cuh"
+#include "predict.cuh"
 
 using namespace mxd;
 
@@ -195,14 +199,128 @@ static int allreduce(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t cou
   return MIXDIR_B200_OK;
 }
 
+// ---------------------------------------------------------------------------
+// block cache: device and page-locked allocations are recycled across handles (cudaMalloc,
+// cudaFree and page-locking cost milliseconds; a host that re-creates handles, e.g. per
+// repetition or per batch, should not pay them every time).  mixdir_b200_release_cache() gives
+// everything back.
+// ---------------------------------------------------------------------------
+namespace cache {
+static std::mutex mu;
+static std::multimap<std::pair<int, size_t>, void*> dev_free;          // (device, bytes) -> block
+static std::unordered_map<void*, std::pair<int, size_t>> dev_live;     // block -> (device, bytes)
+static std::multimap<size_t, void*> pin_free;
+static std::unordered_map<void*, size_t> pin_live;
+static size_t dev_cached = 0;
+static const size_t kDevCap = (size_t)48 << 30;  // beyond this, blocks go back to the driver
+
+static cudaError_t dev_get(void** p, size_t bytes) {
+  bytes = (bytes + 511) & ~(size_t)511;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = dev_free.find({dev, bytes});
+    if (it != dev_free.end()) {
+      *p = it->second;
+      dev_free.erase(it);
+      dev_cached -= bytes;
+      dev_live[*p] = {dev, bytes};
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {  // make room and retry once
+    cudaGetLastError();
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (auto& kv : dev_free) drop.push_back(kv.second);
+      dev_free.clear();
+      dev_cached = 0;
+    }
+    for (void* q : drop) cudaFree(q);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(mu);
+    dev_live[*p] = {dev, bytes};
+  }
+  return e;
+}
+static void dev_put(void* p) {
+  std::pair<int, size_t> k;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = dev_live.find(p);
+    if (it == dev_live.end()) {
+      cudaFree(p);
+      return;
+    }
+    k = it->second;
+    dev_live.erase(it);
+    if (dev_cached + k.second <= kDevCap) {
+      dev_free.insert({k, p});
+      dev_cached += k.second;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+static cudaError_t pin_get(void** p, size_t bytes) {
+  bytes = (bytes + 4095) & ~(size_t)4095;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = pin_free.lower_bound(bytes);
+    if (it != pin_free.end() && it->first <= 2 * bytes + (1 << 16)) {
+      *p = it->second;
+      pin_live[*p] = it->first;
+      pin_free.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(mu);
+    pin_live[*p] = bytes;
+  }
+  return e;
+}
+static void pin_put(void* p) {
+  std::lock_guard<std::mutex> g(mu);
+  auto it = pin_live.find(p);
+  if (it == pin_live.end()) return;
+  pin_free.insert({it->second, p});
+  pin_live.erase(it);
+}
+static void release_all() {
+  std::vector<void*> d, h;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : dev_free) d.push_back(kv.second);
+    for (auto& kv : pin_free) h.push_back(kv.second);
+    dev_free.clear();
+    pin_free.clear();
+    dev_cached = 0;
+  }
+  for (void* q : d) cudaFree(q);
+  for (void* q : h) cudaFreeHost(q);
+}
+}  // namespace cache
+
+extern "C" int mixdir_b200_release_cache(void) {
+  cache::release_all();
+  return MIXDIR_B200_OK;
+}
+
 template <typename T>
 static int dalloc(T** p, size_t n) {
-  CU_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CU_TRY(cache::dev_get((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
   return MIXDIR_B200_OK;
 }
 template <typename T>
 static void dfree(T*& p) {
-  if (p) cudaFree(p);
+  if (p) cache::dev_put((void*)p);
   p = nullptr;
 }
 
@@ -229,9 +347,9 @@ static void free_shard(Shard& s) {
   s.copy_stream = nullptr;
   for (auto e : s.up_ev) cudaEventDestroy(e);
   s.up_ev.clear();
-  if (s.h_status) cudaFreeHost(s.h_status);
+  if (s.h_status) cache::pin_put(s.h_status);
   s.h_status = nullptr;
-  if (s.h_pin) cudaFreeHost(s.h_pin);
+  if (s.h_pin) cache::pin_put(s.h_pin);
   s.h_pin = nullptr;
   for (auto e : s.ev_em) cudaEventDestroy(e);
   s.ev_em.clear();
@@ -280,19 +398,19 @@ static int init_geometry(mixdir_b200_handle* h, int code_bytes, int J, const int
 
 static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   CU_TRY(cudaSetDevice(s.device));
-  cudaDeviceProp prop;
-  CU_TRY(cudaGetDeviceProperties(&prop, s.device));
-  if (prop.major < 9)
+  int cc_major = 0;  // (cudaGetDeviceProperties costs milliseconds; these attribute reads do not)
+  CU_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, s.device));
+  if (cc_major < 10)
     return fail(MIXDIR_B200_CUDA_ERROR, "mixdir_b200 needs a Blackwell-class GPU (built for sm_100a)");
-  s.sm_count = prop.multiProcessorCount;
-  s.smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CU_TRY(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.device));
+  CU_TRY(cudaDeviceGetAttribute(&s.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s.device));
   CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
   RET_IF(dalloc(&s.d_scan, 1));
   CU_TRY(cudaMemsetAsync(s.d_scan, 0, sizeof(ScanOut), s.stream));
   CU_TRY(cudaEventCreate(&s.ev_loop0));
   CU_TRY(cudaEventCreate(&s.ev_loop1));
-  CU_TRY(cudaMallocHost((void**)&s.h_status, sizeof(IterStatus)));
+  CU_TRY(cache::pin_get((void**)&s.h_status, sizeof(IterStatus)));
   const int J = h->J;
   RET_IF(dalloc(&s.d_ncat, J));
   RET_IF(dalloc(&s.d_rowoff, J));
@@ -308,9 +426,14 @@ static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   CU_TRY(cudaMemcpy(s.d_na_row, na.data(), h->NR, cudaMemcpyHostToDevice));
   const size_t bytes = (size_t)(s.n_rows + kRowPad) * h->row_bytes;
   RET_IF(dalloc(&s.d_codes, bytes));
-  // only the pad rows need zeroing; every real row is overwritten by the upload
-  CU_TRY(cudaMemsetAsync(s.d_codes + (size_t)s.n_rows * h->row_bytes, 0,
-                         (size_t)kRowPad * h->row_bytes, s.stream));
+  // Zero what the upload does not write (on the copy stream, i.e. before the copies): the pad
+  // rows always, and the whole buffer when rows carry padding bytes (J*CB not a multiple of 4) --
+  // a stale byte there would be read as a code of a padding feature.
+  if (h->J * h->CB == h->row_bytes)
+    CU_TRY(cudaMemsetAsync(s.d_codes + (size_t)s.n_rows * h->row_bytes, 0,
+                           (size_t)kRowPad * h->row_bytes, s.copy_stream));
+  else
+    CU_TRY(cudaMemsetAsync(s.d_codes, 0, bytes, s.copy_stream));
   return MIXDIR_B200_OK;
 }
 
@@ -427,7 +550,7 @@ static int resolve_scan(mixdir_b200_handle* h) {
     NCCL_TRY(nccl::AllReduce(d + 1, d + 1, 2, nccl::kInt64, nccl::kMax, s.comm, s.stream));
     CU_TRY(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
-    cudaFree(d);
+    dfree(d);
     miss = v[0];
     mx = (int)v[1];
     bad = (int)v[2];
@@ -867,10 +990,10 @@ static int pin_reset(Shard& s, size_t need) {
   CU_TRY(cudaSetDevice(s.device));
   if (s.h_pin_bytes < need) {
     CU_TRY(cudaStreamSynchronize(s.stream));
-    if (s.h_pin) cudaFreeHost(s.h_pin);
+    if (s.h_pin) cache::pin_put(s.h_pin);
     s.h_pin = nullptr;
     s.h_pin_bytes = 0;
-    CU_TRY(cudaHostAlloc((void**)&s.h_pin, need, cudaHostAllocMapped | cudaHostAllocPortable));
+    CU_TRY(cache::pin_get((void**)&s.h_pin, need));
     s.h_pin_bytes = need;
   }
   s.h_pin_used = 0;
@@ -1239,13 +1362,47 @@ static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob,
     int32_t* d_pc = nullptr;
     if (class_prob) RET_IF(dalloc(&d_cp, (size_t)s.n_rows * K));
     if (pred_class) RET_IF(dalloc(&d_pc, (size_t)s.n_rows));
-    PredictArgs a = {s.d_codes, h->row_bytes, s.n_rows, h->J, K, KP, s.d_rowoff, s.d_logU,
-                     s.d_lambda_pad, d_cp, d_pc};
-    const int grid = s.sm_count * 8;
-    if (h->CB == 1)
-      k_predict<1><<<grid, 256, 0, s.stream>>>(a);
-    else
-      k_predict<2><<<grid, 256, 0, s.stream>>>(a);
+    // shared-memory table kernel when K <= 32 and the table fits, else the general kernel
+    const int KC = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+    const int FPW = 4 / h->CB, W = 16, RPW = 32 / KC;
+    const PredictSmem L(h->NR, KC, W, 8, h->WPR, FPW);
+    typedef void (*pfn)(PredictSmemArgs);
+    pfn fn = nullptr;
+    if (K <= 32 && RPW <= FPW * 8 && L.total <= (size_t)s.smem_optin) {
+      if (h->CB == 1) fn = KC == 8 ? k_predict_smem<8, 1> : (KC == 16 ? k_predict_smem<16, 1> : k_predict_smem<32, 1>);
+      else fn = KC == 8 ? k_predict_smem<8, 2> : (KC == 16 ? k_predict_smem<16, 2> : k_predict_smem<32, 2>);
+      if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)L.total) != cudaSuccess) {
+        cudaGetLastError();
+        fn = nullptr;
+      }
+    }
+    if (fn) {
+      const int R = W * 8 * RPW;
+      PredictSmemArgs a;
+      a.codes = reinterpret_cast<const uint32_t*>(s.d_codes);
+      a.n_rows = s.n_rows;
+      a.n_tiles = (int)((s.n_rows + R - 1) / R);
+      a.WPR = h->WPR;
+      a.NR = h->NR;
+      a.K = K;
+      a.KP = KP;
+      a.rowoff_pad = s.d_rowoff_pad;
+      a.logU = s.d_logU;
+      a.lambda = s.d_lambda_pad;
+      a.class_prob = d_cp;
+      a.pred_class = d_pc;
+      const int grid = std::min(s.sm_count, a.n_tiles);
+      fn<<<grid, 32 * W, L.total, s.stream>>>(a);
+    } else {
+      PredictArgs a = {s.d_codes, h->row_bytes, s.n_rows, h->J, K, KP, s.d_rowoff, s.d_logU,
+                       s.d_lambda_pad, d_cp, d_pc};
+      const int grid = s.sm_count * 8;
+      if (h->CB == 1)
+        k_predict<1><<<grid, 256, 0, s.stream>>>(a);
+      else
+        k_predict<2><<<grid, 256, 0, s.stream>>>(a);
+    }
     CU_TRY(cudaGetLastError());
     if (class_prob)  // shard block of an n_rows x K column-major matrix
       CU_TRY(cudaMemcpy2DAsync(class_prob + s.row0, (size_t)h->n_rows * sizeof(double), d_cp,
@@ -1255,8 +1412,8 @@ static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob,
       CU_TRY(cudaMemcpyAsync(pred_class + s.row0, d_pc, (size_t)s.n_rows * sizeof(int32_t),
                              cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
-    if (d_cp) cudaFree(d_cp);
-    if (d_pc) cudaFree(d_pc);
+    dfree(d_cp);
+    dfree(d_pc);
   }
   return MIXDIR_B200_OK;
 }
@@ -1336,7 +1493,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
                                (size_t)s.n_rows * sizeof(double), (size_t)s.n_rows * sizeof(double),
                                K, cudaMemcpyDeviceToHost, s.stream));
       CU_TRY(cudaStreamSynchronize(s.stream));
-      cudaFree(d_zeta);
+      dfree(d_zeta);
     }
     bufs[si] = s.d_stats;
   }
