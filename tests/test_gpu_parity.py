@@ -291,3 +291,23 @@ def test_cluster_shapes_against_oracle(K, J, dp):
         assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
         assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
         assert np.array_equal(r["pred_class"], ref["pred_class"])
+
+
+def test_recycled_buffers_do_not_leak_stale_codes():
+    """Device blocks are recycled across handles (block cache).  A handle whose rows carry padding
+    bytes (J*code_bytes not a multiple of 4) must not see the previous owner's bytes there."""
+    n = 1000
+    big = np.full((n, 8), 250, dtype=np.uint8)  # fills every byte of an (n+512) x 8 block
+    with Engine(big, np.full(8, 250, dtype=np.int32)) as eng:
+        assert eng.max_code == 250
+    ncat = np.array([2, 5, 4, 3, 2], dtype=np.int32)  # J=5 -> 8-byte rows, 3 padding bytes
+    codes, _ = synth.make_codes(3, n, ncat, 3)
+    z0 = synth.zeta_init(3, n, 3)
+    p0 = synth.phi_init(3, ncat, 3)
+    ref = po.fit(po.codes_to_r_matrix(codes), ncat, 3, 0, 1.0, 1.0, 0.1, 6, -np.inf, z0, p0)
+    for engine in (2, 3, 1):
+        with Engine(codes, ncat) as eng:
+            eng.set_engine(engine)
+            r = eng.fit(3, z0.sum(axis=0), p0, max_iter=6, epsilon=-np.inf)
+        assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+        assert np.array_equal(r["pred_class"], ref["pred_class"])
