@@ -197,12 +197,26 @@ typedef struct mixdir_b200_timing {
   int cluster_size;     /* fused: P */
   int grid_ctas;        /* fused: CTAs launched */
   int smem_bytes;       /* fused: dynamic shared memory per CTA */
+  int unit_elements;    /* fused: gather/scatter elements per row (features, pairs, padding) */
+  int unit_pairs;       /* fused: features combined two-by-two into one element */
+  int unit_table_rows;  /* fused: rows of the unit tables (sum over elements of their codes) */
 } mixdir_b200_timing;
 
 int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out);
 /* 0 = automatic (default), 1 = generic kernel only, 2 = fused kernel or fail,
  * 3 = bucketed fused kernel or fail */
 int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine);
+/* Feature pairing of the fused kernel (default on): two features share one table gather and one
+ * histogram update where shared memory allows.  Results change only by floating-point
+ * re-association inside the per-row logit sum (mixdir_impl.cpp:77-82).  0 switches it off. */
+int mixdir_b200_set_pairing(mixdir_b200_handle* h, int on);
+/* Diagnostic, host only (no device): the unit plan with n_pairs feature pairs for 1-byte codes.
+ * desc: n_elements x {byte offset of feature a (<0: padding), of feature b (<0: single), C_b+1, 0};
+ * gbase: first unit-table row of each element; t2src: n_table_rows x {feature-table row a, row b or
+ * -1} (only written when n_pairs > 0); marg: sum_j(C_j+1) x {start, stride, count, 0}: the unit rows a
+ * feature-table row collects.  Output arrays may be NULL. */
+int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, int* n_elements,
+                          int* n_table_rows, int* desc, int* gbase, int* t2src, int* marg);
 
 const char* mixdir_b200_last_error(void);
 int mixdir_b200_abi_version(void);

@@ -22,7 +22,9 @@ SYMBOLS = [
     "mixdir_b200_create_dist", "mixdir_b200_destroy", "mixdir_b200_release_cache",
     "mixdir_b200_n_rows", "mixdir_b200_max_code", "mixdir_b200_n_missing", "mixdir_b200_fit",
     "mixdir_b200_predict", "mixdir_b200_estep", "mixdir_b200_last_timing",
-    "mixdir_b200_set_engine", "mixdir_b200_last_error", "mixdir_b200_abi_version",
+    "mixdir_b200_set_engine", "mixdir_b200_set_pairing", "mixdir_b200_unit_plan",
+    "mixdir_b200_last_error",
+    "mixdir_b200_abi_version",
 ]
 
 
@@ -36,7 +38,8 @@ class Timing(C.Structure):
     _fields_ = [("fit_loop_ms", C.c_double), ("em_kernel_ms", C.c_double),
                 ("iterations", C.c_int), ("em_launches", C.c_int), ("total_launches", C.c_int),
                 ("engine", C.c_int), ("classes_per_cta", C.c_int), ("cluster_size", C.c_int),
-                ("grid_ctas", C.c_int), ("smem_bytes", C.c_int)]
+                ("grid_ctas", C.c_int), ("smem_bytes", C.c_int), ("unit_elements", C.c_int),
+                ("unit_pairs", C.c_int), ("unit_table_rows", C.c_int)]
 
 
 _lib = None
@@ -72,6 +75,8 @@ def lib():
     L.mixdir_b200_estep.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, dp, ip, vp]
     L.mixdir_b200_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.mixdir_b200_set_engine.argtypes = [vp, C.c_int]
+    L.mixdir_b200_set_pairing.argtypes = [vp, C.c_int]
+    L.mixdir_b200_unit_plan.argtypes = [C.c_int, ip, C.c_int, ip, ip, vp, vp, vp, vp]
     L.mixdir_b200_last_error.restype = C.c_char_p
     L.mixdir_b200_abi_version.restype = C.c_int
     _lib = L

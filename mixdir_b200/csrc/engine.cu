@@ -114,6 +114,21 @@ static int load() {
 // ---------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------
+// What the fused kernels gather/scatter: one element per feature, or per PAIR of features
+// (kernels.cuh "Units").  identity: elements == (padded) features, the raw code matrix and the
+// feature tables are used as they are.
+struct UnitPlan {
+  bool identity = true;
+  int U = 0;      // elements per packed row, padding included (multiple of 4 when packed)
+  int WPRu = 0;   // 32-bit words per (packed) row
+  int NR2 = 0;    // rows of the unit tables
+  int n_pairs = 0;
+  std::vector<UnitDesc> desc;  // [U]
+  std::vector<int> gbase;      // [U] first unit-table row of element e
+  std::vector<int2> t2src;     // [NR2] feature-table rows a unit row is the sum of
+  std::vector<MargDesc> marg;  // [NR]  unit rows a feature-table row collects
+};
+
 struct Plan {
   int engine = 0;  // 1 generic, 2 fused
   int KP = 0;
@@ -121,6 +136,7 @@ struct Plan {
   int n_clusters = 0;
   size_t smem = 0;
   int R = 0;  // rows per tile
+  UnitPlan up;
 };
 
 struct Shard {
@@ -144,6 +160,17 @@ struct Shard {
   double *d_lambda_pad = nullptr, *d_prior_out = nullptr;
   double *d_Spart = nullptr, *d_cspart = nullptr, *d_Hpart = nullptr;
   int *d_perm = nullptr, *d_underflow = nullptr, *d_warn = nullptr;
+  // units (feature pairs): descriptors + packed codes, kept while the plan stays the same
+  std::vector<UnitDesc> unit_sig;  // plan the buffers below were built for
+  bool unit_valid = false;
+  UnitDesc* d_udesc = nullptr;
+  int* d_ugbase = nullptr;
+  int2* d_t2src = nullptr;
+  MargDesc* d_marg = nullptr;
+  uint8_t* d_ucodes = nullptr;     // [n_rows + kRowPad][WPRu] words (null: identity plan)
+  int64_t packed_rows = 0;         // rows of d_ucodes already packed
+  double* d_T2 = nullptr;          // [NR2][KP] (workspace)
+  int ws_NR2 = 0;
   PriorState* d_prior = nullptr;
   IterStatus* d_status = nullptr;
   IterStatus* h_status = nullptr;  // pinned
@@ -174,6 +201,7 @@ struct mixdir_b200_handle {
   std::vector<Shard> shards;
   int rank = 0, world = 1;   // multi-process flavour
   int engine_pref = 0;
+  int pairing = 1;           // 1: pair features into units where shared memory allows (default)
   bool scan_resolved = false;
   mixdir_b200_timing timing = {};
 };
@@ -329,8 +357,8 @@ static void free_workspace(Shard& s) {
   dfree(s.d_cs_a); dfree(s.d_cs_b); dfree(s.d_pieces); dfree(s.d_trace); dfree(s.d_rag_a);
   dfree(s.d_rag_b); dfree(s.d_lambda); dfree(s.d_lambda_pad); dfree(s.d_prior_out);
   dfree(s.d_Spart); dfree(s.d_cspart); dfree(s.d_Hpart); dfree(s.d_perm);
-  dfree(s.d_underflow); dfree(s.d_warn); dfree(s.d_prior); dfree(s.d_status);
-  s.ws_K = s.ws_KP = s.ws_iter = s.ws_clusters = s.ws_ctas = 0;
+  dfree(s.d_underflow); dfree(s.d_warn); dfree(s.d_prior); dfree(s.d_status); dfree(s.d_T2);
+  s.ws_K = s.ws_KP = s.ws_iter = s.ws_clusters = s.ws_ctas = s.ws_NR2 = 0;
 }
 
 static void free_shard(Shard& s) {
@@ -340,6 +368,8 @@ static void free_shard(Shard& s) {
   free_workspace(s);
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
   dfree(s.d_ragoff); dfree(s.d_na_row); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
+  dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
+  s.unit_valid = false;
   if (s.copy_stream) {
     cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
     cudaStreamDestroy(s.copy_stream);
@@ -766,6 +796,11 @@ extern "C" int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine) {
   h->engine_pref = engine;
   return MIXDIR_B200_OK;
 }
+extern "C" int mixdir_b200_set_pairing(mixdir_b200_handle* h, int on) {
+  if (!h) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL handle");
+  h->pairing = on ? 1 : 0;
+  return MIXDIR_B200_OK;
+}
 extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out) {
   if (!h || !out) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   *out = h->timing;
@@ -842,7 +877,98 @@ static int plan_occupancy(const mixdir_b200_handle* h, const Shard& s, const Pla
   return nclus;
 }
 
-// engine 2: k_em_fused (row-owned M-step, read-modify-write per row and feature)
+// identity unit plan: one element per (padded) feature, raw codes, feature tables
+static void identity_units(const mixdir_b200_handle* h, UnitPlan* up) {
+  *up = UnitPlan();
+  up->identity = true;
+  up->U = (int)h->rowoff_pad.size();
+  up->WPRu = h->WPR;
+  up->NR2 = h->NR;
+  up->gbase = h->rowoff_pad;
+  up->desc.assign(up->U, UnitDesc{-1, -1, 1, 0});
+  for (int j = 0; j < h->J; j++) up->desc[j] = UnitDesc{j * h->CB, -1, 1, 0};
+  up->marg.assign(h->NR, MargDesc{0, 0, 0, 0});
+  for (int j = 0; j < h->J; j++)
+    for (int c = 1; c <= h->ncat[j]; c++) up->marg[h->rowoff[j] + c] = MargDesc{h->rowoff[j] + c, 0, 1, 0};
+}
+
+// Unit plan with m feature pairs (1-byte codes only).  The 2m features with the fewest
+// categories are paired smallest-with-largest, which minimises the added table rows
+// sum (C_a+1)(C_b+1) for that many pairs; every pair code must still fit a byte.
+// Returns false if some pair would need more than 256 codes.
+static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up) {
+  const int J = h->J;
+  if (m <= 0) {
+    identity_units(h, up);
+    return true;
+  }
+  if (h->CB != 1 || 2 * m > J) return false;
+  std::vector<int> order(J);
+  for (int j = 0; j < J; j++) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->ncat[a] < h->ncat[b]; });
+  std::vector<int> partner(J, -1);
+  for (int i = 0; i < m; i++) {
+    const int a = order[i], b = order[2 * m - 1 - i];
+    if ((h->ncat[a] + 1) * (h->ncat[b] + 1) > 256) return false;
+    partner[a] = b;
+    partner[b] = a;
+  }
+  *up = UnitPlan();
+  up->identity = false;
+  up->n_pairs = m;
+  up->marg.assign(h->NR, MargDesc{0, 0, 0, 0});
+  int nr2 = 0;
+  for (int j = 0; j < J; j++) {
+    const int b = partner[j];
+    if (b >= 0 && b < j) continue;  // emitted with its lower-index partner
+    const int Ca = h->ncat[j];
+    if (b < 0) {
+      up->desc.push_back(UnitDesc{j, -1, 1, 0});
+      up->gbase.push_back(nr2);
+      for (int c = 0; c <= Ca; c++) up->t2src.push_back(make_int2(h->rowoff[j] + c, -1));
+      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c, 0, 1, 0};
+      nr2 += Ca + 1;
+    } else {
+      const int Cb = h->ncat[b], mul = Cb + 1;
+      up->desc.push_back(UnitDesc{j, b, mul, 0});
+      up->gbase.push_back(nr2);
+      for (int ca = 0; ca <= Ca; ca++)
+        for (int cb = 0; cb <= Cb; cb++)
+          up->t2src.push_back(make_int2(h->rowoff[j] + ca, h->rowoff[b] + cb));
+      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c * mul, 1, mul, 0};
+      for (int c = 1; c <= Cb; c++) up->marg[h->rowoff[b] + c] = MargDesc{nr2 + c, mul, Ca + 1, 0};
+      nr2 += (Ca + 1) * mul;
+    }
+  }
+  up->NR2 = nr2;
+  while (up->desc.size() % 4) {  // padding elements: code 0 -> the all-NA row of element 0 (scratch)
+    up->desc.push_back(UnitDesc{-1, -1, 1, 0});
+    up->gbase.push_back(up->gbase[0]);
+  }
+  up->U = (int)up->desc.size();
+  up->WPRu = up->U / 4;
+  return true;
+}
+
+// host-only view of a unit plan (no device needed): lets the CPU tests check the invariants
+// the device code relies on.  Arrays may be NULL (sizes only).
+extern "C" int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, int* n_elements,
+                                     int* n_table_rows, int* desc, int* gbase, int* t2src, int* marg) {
+  mixdir_b200_handle h;
+  RET_IF(init_geometry(&h, 1, n_features, ncat));
+  UnitPlan up;
+  if (n_pairs < 0 || !make_units(&h, n_pairs, &up))
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "this many pairs cannot be formed (a pair code must fit a byte)");
+  if (n_elements) *n_elements = up.U;
+  if (n_table_rows) *n_table_rows = up.NR2;
+  if (desc) memcpy(desc, up.desc.data(), up.desc.size() * sizeof(UnitDesc));
+  if (gbase) memcpy(gbase, up.gbase.data(), up.gbase.size() * sizeof(int));
+  if (t2src && !up.identity) memcpy(t2src, up.t2src.data(), up.t2src.size() * sizeof(int2));
+  if (marg) memcpy(marg, up.marg.data(), up.marg.size() * sizeof(MargDesc));
+  return MIXDIR_B200_OK;
+}
+
+// engine 2: k_em_fused (row-owned M-step, read-modify-write per row and unit)
 static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
   Plan best;
   double best_cost = 1e300;
@@ -852,21 +978,51 @@ static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
     if (RPW > FPW) continue;
     const int P = (K + KC - 1) / KC;
     if (P > 8) continue;
-    const int RG = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
-    const int W = std::min(16, h->WPR);
-    FusedSmem L(h->NR, KC, W, RG, h->WPR, FPW, P);
-    if (L.total > (size_t)s.smem_optin) continue;
-    // cost ~ shared-memory wavefronts per row: P CTAs x (1 / rows-per-instruction) x conflict factor
+    const int RG0 = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
+    // most feature pairs whose unit tables (+ tiles) still fit shared memory
+    UnitPlan up;
+    bool found = false;
+    int W = 0, RG = RG0;
+    size_t smem = 0;
+    // a row tile is one bulk copy: its byte count (and the second buffer's offset) must be a
+    // multiple of 16
+    auto shape = [&](const UnitPlan& u) {
+      W = std::min(16, u.WPRu);
+      RG = RG0;
+      while (((size_t)W * RG * RPW * u.WPRu) % 4 != 0 && RG < 8) RG *= 2;
+      return FusedSmem(u.NR2, KC, W, RG, u.WPRu, FPW, P);
+    };
+    for (int m = (h->pairing && h->CB == 1) ? h->J / 2 : 0; m >= 0; m--) {
+      if (!make_units(h, m, &up)) continue;
+      FusedSmem L = shape(up);
+      if (L.total > (size_t)s.smem_optin) continue;
+      // fewer pairs that still give the same number of code words per row: smaller tables
+      const int m_min = std::max(0, h->J - 4 * up.WPRu);
+      if (m > 0 && m_min < m && make_units(h, m_min, &up)) {
+        L = shape(up);
+      } else if (m > 0) {
+        make_units(h, m, &up);
+        L = shape(up);
+      }
+      smem = L.total;
+      found = true;
+      break;
+    }
+    if (!found) continue;
+    Plan c;
+    c.engine = 2; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
+    c.smem = smem; c.R = W * RG * RPW;
+    c.n_clusters = plan_occupancy(h, s, c);
+    if (c.n_clusters < 1) continue;
+    // cost ~ shared-memory wavefronts per row over the SMs in use: P CTAs x elements per row /
+    // rows per instruction x conflict factor
     const double conflict = KC == 8 ? 1.5 : 1.0;
-    const double cost = P * conflict / RPW + 1e-3 * P;
+    const double used = std::min(1.0, (double)c.n_clusters * P / s.sm_count);
+    const double cost = P * conflict * (up.WPRu * FPW) / RPW / used + 1e-3 * P;
     if (cost < best_cost) {
-      Plan c;
-      c.engine = 2; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
-      c.smem = L.total; c.R = W * RG * RPW;
-      c.n_clusters = plan_occupancy(h, s, c);
-      if (c.n_clusters < 1) continue;
       best_cost = cost;
       best = c;
+      best.up = up;
     }
   }
   if (best.engine != 2) return false;
@@ -902,6 +1058,7 @@ static bool plan_bucket(const mixdir_b200_handle* h, const Shard& s, int K, Plan
         Plan c;
         c.engine = 3; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
         c.smem = L.total; c.R = R;
+        identity_units(h, &c.up);
         c.n_clusters = plan_occupancy(h, s, c);
         if (c.n_clusters < 1) continue;
         best_cost = cost;
@@ -929,6 +1086,7 @@ static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) 
   Plan g;
   g.engine = 1;
   g.KP = (K + 7) & ~7;
+  identity_units(h, &g.up);
   *out = g;
   return MIXDIR_B200_OK;
 }
@@ -939,10 +1097,11 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   const int nclus = pl.engine >= 2 ? pl.n_clusters : 0;
   const int nctas = nclus * pl.P;
   if (s.ws_K == K && s.ws_KP == KP && s.ws_iter >= max_iter && s.ws_clusters >= nclus &&
-      s.ws_ctas >= nctas)
+      s.ws_ctas >= nctas && s.ws_NR2 >= pl.up.NR2)
     return MIXDIR_B200_OK;
   free_workspace(s);
   const size_t tab = (size_t)h->NR * KP;
+  const size_t tab2 = (size_t)pl.up.NR2 * KP;
   const size_t rag = (size_t)h->sum_ncat * K;
   RET_IF(dalloc(&s.d_T, tab));
   RET_IF(dalloc(&s.d_phi, tab));
@@ -964,7 +1123,7 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   RET_IF(dalloc(&s.d_prior, 1));
   RET_IF(dalloc(&s.d_status, 1));
   if (nclus > 0) {
-    RET_IF(dalloc(&s.d_Spart, (size_t)nclus * tab));
+    RET_IF(dalloc(&s.d_Spart, (size_t)nclus * tab2));
     RET_IF(dalloc(&s.d_cspart, (size_t)nclus * KP));
     RET_IF(dalloc(&s.d_Hpart, nctas));
   }
@@ -976,6 +1135,8 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   s.ws_iter = std::max(max_iter, 1);
   s.ws_clusters = nclus;
   s.ws_ctas = nctas;
+  RET_IF(dalloc(&s.d_T2, tab2));
+  s.ws_NR2 = pl.up.NR2;
   return MIXDIR_B200_OK;
 }
 
@@ -1022,6 +1183,71 @@ static int upload_ragoff(mixdir_b200_handle* h, Shard& s, int K) {
   return pin_send(s, s.d_ragoff, ro.data(), h->J * sizeof(int64_t));
 }
 
+static size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
+static size_t unit_stage_bytes(const UnitPlan& up) {
+  return pad8(up.desc.size() * sizeof(UnitDesc)) + pad8(up.gbase.size() * sizeof(int)) +
+         pad8(up.t2src.size() * sizeof(int2)) + pad8(up.marg.size() * sizeof(MargDesc)) + 4 * 64;
+}
+
+template <typename T>
+static int send_vec(Shard& s, T** dptr, const std::vector<T>& vec) {
+  const size_t bytes = pad8(vec.size() * sizeof(T));
+  RET_IF(dalloc((unsigned char**)dptr, bytes));
+  std::vector<unsigned char> tmp(bytes, 0);
+  memcpy(tmp.data(), vec.data(), vec.size() * sizeof(T));
+  return pin_send(s, *dptr, tmp.data(), bytes);
+}
+
+// Device copies of the unit plan (+ the packed code buffer) for this shard; kept across fits
+// while the plan stays the same.  Call after pin_reset (the arrays go through the staging area).
+static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
+  const UnitPlan& up = pl.up;
+  CU_TRY(cudaSetDevice(s.device));
+  if (s.unit_valid && s.unit_sig.size() == up.desc.size() &&
+      memcmp(s.unit_sig.data(), up.desc.data(), up.desc.size() * sizeof(UnitDesc)) == 0)
+    return MIXDIR_B200_OK;
+  s.unit_valid = false;
+  dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
+  s.packed_rows = 0;
+  RET_IF(send_vec(s, &s.d_udesc, up.desc));
+  RET_IF(send_vec(s, &s.d_ugbase, up.gbase));
+  RET_IF(send_vec(s, &s.d_marg, up.marg));
+  if (!up.identity) {
+    RET_IF(send_vec(s, &s.d_t2src, up.t2src));
+    const size_t rowb = (size_t)up.WPRu * 4;
+    RET_IF(dalloc(&s.d_ucodes, (size_t)(s.n_rows + kRowPad) * rowb));
+    CU_TRY(cudaMemsetAsync(s.d_ucodes + (size_t)s.n_rows * rowb, 0, (size_t)kRowPad * rowb, s.stream));
+  }
+  s.unit_sig = up.desc;
+  s.unit_valid = true;
+  return MIXDIR_B200_OK;
+}
+
+// pack raw rows [packed_rows, upto) into unit codes (their upload must have been consumed)
+static int pack_units(mixdir_b200_handle* h, Shard& s, const Plan& pl, int64_t upto, int* launches) {
+  if (pl.up.identity || s.packed_rows >= upto) return MIXDIR_B200_OK;
+  const int64_t r0 = s.packed_rows, nr = upto - r0;
+  const int WPRu = pl.up.WPRu;
+  const int grid = (int)std::min<int64_t>((int64_t)s.sm_count * 16, (nr * WPRu + 255) / 256);
+  k_pack_units<<<grid, 256, 0, s.stream>>>(s.d_codes + (size_t)r0 * h->row_bytes, h->row_bytes, nr,
+                                           s.d_udesc, WPRu,
+                                           reinterpret_cast<uint32_t*>(s.d_ucodes) + (size_t)r0 * WPRu);
+  CU_TRY(cudaGetLastError());
+  s.packed_rows = upto;
+  if (launches) *launches += 1;
+  return MIXDIR_B200_OK;
+}
+
+// unit table T2 from the feature table T (after every k_param)
+static int build_unit_table(Shard& s, const Plan& pl) {
+  if (pl.up.identity) return MIXDIR_B200_OK;
+  const size_t n = (size_t)pl.up.NR2 * pl.KP;
+  const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)s.sm_count * 4);
+  k_build_T2<<<grid, 256, 0, s.stream>>>(s.d_t2src, pl.up.NR2, pl.KP, s.d_T, s.d_T2);
+  CU_TRY(cudaGetLastError());
+  return MIXDIR_B200_OK;
+}
+
 // One E+M pass on a shard: statistics land in s.d_stats (local, before any all-reduce).
 // While an asynchronous upload is still in flight the pass runs CHUNKED: the compute stream
 // waits for upload chunk c (and scans it), then launches the kernel on the rows that are
@@ -1030,6 +1256,10 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
                      bool scatter, cudaEvent_t ev0, cudaEvent_t ev1, int* launches) {
   CU_TRY(cudaSetDevice(s.device));
   const size_t tab = (size_t)h->NR * pl.KP;
+  const size_t tab2 = (size_t)pl.up.NR2 * pl.KP;
+  const UnitPlan& up = pl.up;
+  const uint8_t* ucodes = up.identity ? s.d_codes : s.d_ucodes;
+  const size_t urow_bytes = up.identity ? (size_t)h->row_bytes : (size_t)up.WPRu * 4;
   CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
   // row ranges of this pass: one per pending upload chunk, else the whole shard
   std::vector<std::pair<int64_t, int64_t>> ranges;
@@ -1055,7 +1285,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
 
   if (pl.engine >= 2 && s.n_rows > 0) {
     if (chunked) {  // partial buffers accumulate over the launches
-      CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab * sizeof(double), s.stream));
+      CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab2 * sizeof(double), s.stream));
       CU_TRY(cudaMemsetAsync(s.d_cspart, 0, (size_t)pl.n_clusters * pl.KP * sizeof(double), s.stream));
       CU_TRY(cudaMemsetAsync(s.d_Hpart, 0, (size_t)pl.n_clusters * pl.P * sizeof(double), s.stream));
     }
@@ -1065,20 +1295,21 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       if (range_chunk[i] != SIZE_MAX) RET_IF(consume_upload(h, s, range_chunk[i]));
       const int64_t r0 = ranges[i].first, nr = ranges[i].second - ranges[i].first;
       if (nr <= 0) continue;
+      RET_IF(pack_units(h, s, pl, ranges[i].second, launches));
       const int n_tiles = (int)((nr + pl.R - 1) / pl.R);
       const int nclus = std::min(pl.n_clusters, n_tiles);
       max_clus = std::max(max_clus, nclus);
       FusedArgs a;
-      a.codes = reinterpret_cast<const uint32_t*>(s.d_codes + (size_t)r0 * h->row_bytes);
+      a.codes = reinterpret_cast<const uint32_t*>(ucodes + (size_t)r0 * urow_bytes);
       a.n_rows = nr;
       a.n_tiles = n_tiles;
-      a.WPR = h->WPR;
-      a.NR = h->NR;
+      a.WPR = up.WPRu;
+      a.NR = up.NR2;
       a.K = K;
       a.KP = pl.KP;
       a.P = pl.P;
-      a.rowoff_pad = s.d_rowoff_pad;
-      a.T = s.d_T;
+      a.rowoff_pad = s.d_ugbase;
+      a.T = up.identity ? s.d_T : s.d_T2;
       a.logprior = s.d_logprior;
       a.Spart = s.d_Spart;
       a.cspart = s.d_cspart;
@@ -1111,8 +1342,9 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       *launches += 1;
     }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
-    ReduceArgs r;
+    ReduceUnitsArgs r;
     r.NR = h->NR;
+    r.NR2 = up.NR2;
     r.KP = pl.KP;
     r.n_clusters = chunked ? pl.n_clusters : max_clus;
     r.n_ctas = r.n_clusters * pl.P;
@@ -1121,10 +1353,10 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
     r.Hpart = s.d_Hpart;
     r.underflow = s.d_underflow;
     r.scan = s.d_scan;
-    r.na_row = s.d_na_row;
+    r.marg = s.d_marg;
     r.stats = s.d_stats;
     const int rgrid = (int)std::min<size_t>((tab + 255) / 256, (size_t)s.sm_count * 4);
-    k_reduce_partials<<<rgrid, 256, 0, s.stream>>>(r);
+    k_reduce_units<<<rgrid, 256, 0, s.stream>>>(r);
     CU_TRY(cudaGetLastError());
     *launches += 1;
     h->timing.grid_ctas = max_clus * pl.P;
@@ -1205,12 +1437,16 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   h->timing.classes_per_cta = pl.KC;
   h->timing.cluster_size = pl.P;
   h->timing.smem_bytes = (int)pl.smem;
+  h->timing.unit_elements = pl.up.U;
+  h->timing.unit_pairs = pl.up.n_pairs;
+  h->timing.unit_table_rows = pl.up.NR2;
 
   // ---- initial state on every shard: class masses + table from phi_init ----
   for (auto& s : h->shards) {
     RET_IF(ensure_workspace(h, s, K, pl, p->max_iter));
-    RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096));
+    RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096 + unit_stage_bytes(pl.up)));
     RET_IF(upload_ragoff(h, s, K));
+    RET_IF(ensure_units(h, s, pl));
     while ((int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreate(&e));
@@ -1226,6 +1462,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
                     nullptr, nullptr, s.d_phi, s.d_T, nullptr, s.d_perm};
     k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
     CU_TRY(cudaGetLastError());
+    RET_IF(build_unit_table(s, pl));
   }
 
   // ---- the coordinate-ascent loop (R/mixdir_vi.R:58-115) ----
@@ -1255,6 +1492,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
       ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
                       s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
       k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
+      RET_IF(build_unit_table(s, pl));
       FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, s.d_stats + tab + pl.KP + 2,
                          s.d_stats + tab + pl.KP + 3, s.d_pieces, s.d_stats + tab,
                          s.d_stats + tab + pl.KP, s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior,
@@ -1263,7 +1501,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
       CU_TRY(cudaGetLastError());
       std::swap(s.d_cs_a, s.d_cs_b);
       if (si == 0) {
-        launches += 2;
+        launches += pl.up.identity ? 2 : 3;
         CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(IterStatus), cudaMemcpyDeviceToHost, s.stream));
       }
     }
@@ -1469,13 +1707,15 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   for (size_t si = 0; si < h->shards.size(); si++) {
     Shard& s = h->shards[si];
     RET_IF(ensure_workspace(h, s, K, pl, 1));
-    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096));
+    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096 + unit_stage_bytes(pl.up)));
     RET_IF(upload_ragoff(h, s, K));
+    RET_IF(ensure_units(h, s, pl));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_T, 0, 0.0};
     k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
     CU_TRY(cudaGetLastError());
+    RET_IF(build_unit_table(s, pl));
     CU_TRY(cudaStreamSynchronize(s.stream));
     int l = 0;
     double* d_zeta = nullptr;
@@ -1517,5 +1757,8 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   h->timing.classes_per_cta = pl.KC;
   h->timing.cluster_size = pl.P;
   h->timing.smem_bytes = (int)pl.smem;
+  h->timing.unit_elements = pl.up.U;
+  h->timing.unit_pairs = pl.up.n_pairs;
+  h->timing.unit_table_rows = pl.up.NR2;
   return MIXDIR_B200_OK;
 }

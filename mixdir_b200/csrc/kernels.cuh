@@ -560,6 +560,116 @@ __global__ void k_reduce_partials(ReduceArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Units: what the fused kernels gather and scatter is a UNIT -- one feature, or a PAIR of
+// features (ja, jb) whose codes are combined at upload into one byte
+//     u = x_a * (C_b + 1) + x_b            (0 = both NA),
+// so that one table gather / one histogram read-modify-write serves two features:
+//     T2[u] = T[ja, x_a] + T[jb, x_b],     S[ja, x] = sum_{x_b} S2[x * (C_b + 1) + x_b],  etc.
+// This halves the shared-memory traffic per code; the price is table rows
+// ((C_a+1)(C_b+1) instead of C_a + C_b + 2), so the host planner pairs as many features as the
+// shared-memory budget allows (engine.cu: make_units).  Results change only by the
+// re-association (T_a + T_b) inside the per-row logit sum.
+// ---------------------------------------------------------------------------
+struct UnitDesc {
+  int off_a;  // byte offset of feature ja inside a raw code row; < 0: padding element (code 0)
+  int off_b;  // byte offset of feature jb; < 0: single feature
+  int mul;    // C_b + 1 (1 for a single feature)
+  int pad;
+};
+
+// raw row-major codes (1 byte per cell) -> unit codes, WPRu 32-bit words per row
+__global__ void k_pack_units(const uint8_t* __restrict__ raw, int row_bytes, int64_t n_rows,
+                             const UnitDesc* __restrict__ units, int WPRu, uint32_t* __restrict__ out) {
+  const int64_t total = n_rows * WPRu;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = w / WPRu;
+    const int col = (int)(w - row * WPRu);
+    const uint8_t* r = raw + row * row_bytes;
+    uint32_t cw = 0;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int4 uu = __ldg(reinterpret_cast<const int4*>(units) + col * 4 + f);
+      const UnitDesc u = {uu.x, uu.y, uu.z, uu.w};
+      uint32_t c = 0;
+      if (u.off_a >= 0) {
+        c = r[u.off_a];
+        if (u.off_b >= 0) c = c * (uint32_t)u.mul + r[u.off_b];
+      }
+      cw |= (c & 0xffu) << (8 * f);
+    }
+    out[w] = cw;
+  }
+}
+
+// unit table from the feature table: T2[g2][k] = T[src.x][k] + T[src.y][k]  (src.y < 0: single)
+__global__ void k_build_T2(const int2* __restrict__ src, int NR2, int KP, const double* __restrict__ T,
+                           double* __restrict__ T2) {
+  const size_t n = (size_t)NR2 * KP;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int g2 = (int)(e / KP), k = (int)(e - (size_t)g2 * KP);
+    const int2 s = __ldg(&src[g2]);
+    double v = T[(size_t)s.x * KP + k];
+    if (s.y >= 0) v += T[(size_t)s.y * KP + k];
+    T2[e] = v;
+  }
+}
+
+// feature-table row g = (j, x) collects the unit rows start + i*stride, i < count
+// (count 0: NA row, its statistics are never used)
+struct MargDesc {
+  int start, stride, count, pad;
+};
+
+// deterministic reduction of the per-cluster partials over clusters AND over the partner
+// feature's codes: unit statistics S2 -> feature statistics S
+struct ReduceUnitsArgs {
+  int NR, NR2, KP;
+  int n_clusters, n_ctas;
+  const double* Spart;   // [n_clusters][NR2*KP]
+  const double* cspart;  // [n_clusters][KP]
+  const double* Hpart;   // [n_ctas]
+  const int* underflow;
+  const ScanOut* scan;
+  const MargDesc* marg;  // [NR]
+  double* stats;
+};
+__global__ void k_reduce_units(ReduceUnitsArgs a) {
+  const size_t n = (size_t)a.NR * a.KP;
+  const size_t n2 = (size_t)a.NR2 * a.KP;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(e / a.KP), k = (int)(e - (size_t)g * a.KP);
+    const int4 mm = __ldg(reinterpret_cast<const int4*>(a.marg) + g);
+    const MargDesc m = {mm.x, mm.y, mm.z, mm.w};
+    double s = 0;
+    for (int i = 0; i < m.count; i++) {
+      const size_t e2 = (size_t)(m.start + i * m.stride) * a.KP + k;
+      double t = 0;
+      for (int c = 0; c < a.n_clusters; c++) t += a.Spart[(size_t)c * n2 + e2];
+      s += t;
+    }
+    a.stats[e] = s;
+  }
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < a.KP; k += blockDim.x) {
+      double s = 0;
+      for (int c = 0; c < a.n_clusters; c++) s += a.cspart[(size_t)c * a.KP + k];
+      a.stats[n + k] = s;
+    }
+    if (threadIdx.x == 0) {
+      double h = 0;
+      for (int c = 0; c < a.n_ctas; c++) h += a.Hpart[c];
+      a.stats[n + a.KP] = h;
+      a.stats[n + a.KP + 1] = (*a.underflow) ? 1.0 : 0.0;
+      a.stats[n + a.KP + 2] = (double)a.scan->n_missing;
+      a.stats[n + a.KP + 3] = a.scan->bad ? 1.0 : 0.0;
+    }
+  }
+}
+
 // tail of the statistics buffer for the generic kernel: [underflow | nNA | bad]
 __global__ void k_tail_to_stats(const int* underflow, const ScanOut* scan, double* slot) {
   slot[0] = (*underflow) ? 1.0 : 0.0;

@@ -154,6 +154,10 @@ class Engine:
     def set_engine(self, engine: int):
         _check(_capi.lib().mixdir_b200_set_engine(self._h, engine))
 
+    def set_pairing(self, on: bool):
+        """feature pairing of the fused kernel (default on)"""
+        _check(_capi.lib().mixdir_b200_set_pairing(self._h, 1 if on else 0))
+
     def ragged_size(self, K):
         return int(K * self.ncat.sum())
 

@@ -311,3 +311,35 @@ def test_recycled_buffers_do_not_leak_stale_codes():
             r = eng.fit(3, z0.sum(axis=0), p0, max_iter=6, epsilon=-np.inf)
         assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
         assert np.array_equal(r["pred_class"], ref["pred_class"])
+
+
+@pytest.mark.parametrize("K,J,p_na", [(32, 60, 0.0), (32, 60, 0.1), (10, 23, 0.05), (64, 100, 0.0),
+                                      (3, 5, 0.0), (7, 2, 0.2), (12, 61, 0.0)])
+def test_feature_pair_units_against_oracle(K, J, p_na):
+    """Feature pairing (two features per table gather / histogram update, kernels.cuh "Units"):
+    the same fit with pairing on and off, both against the literal oracle; the pair plan must
+    really be in use for the BASELINE S4 shape."""
+    pat = np.array(([16, 12, 8, 4, 2, 10] * 20)[:J], dtype=np.int32)
+    N = 2500
+    codes, _ = synth.make_codes(21, N, pat, min(K, 16), p_na=p_na)
+    z0 = synth.zeta_init(5, N, K)
+    p0 = synth.phi_init(5, pat, K)
+    ref = po.fit(po.codes_to_r_matrix(codes), pat, K, 0, 1.0, 1.0, 0.1, 5, -np.inf, z0, p0)
+    pairs = {}
+    for on in (True, False):
+        with Engine(codes, pat) as eng:
+            eng.set_engine(2)
+            eng.set_pairing(on)
+            r = eng.fit(K, z0.sum(axis=0), p0, max_iter=5, epsilon=-np.inf)
+            t = eng.timing()
+            # a second fit on the same handle reuses the packed unit codes
+            r2 = eng.fit(K, z0.sum(axis=0), p0, max_iter=5, epsilon=-np.inf)
+        pairs[on] = t["unit_pairs"]
+        assert np.array_equal(r["convergence"], r2["convergence"])
+        assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+        assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
+        assert np.array_equal(r["pred_class"], ref["pred_class"])
+        np.testing.assert_allclose(r["phi"], ref["phi"], rtol=1e-10, atol=1e-10)
+    assert pairs[False] == 0
+    if (J + 3) // 4 > (J - J // 2 + 3) // 4:  # pairing is used when it saves code words per row
+        assert pairs[True] > 0, pairs

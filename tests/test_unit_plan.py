@@ -1,0 +1,99 @@
+"""CPU tests of the feature-pair unit plan (mixdir_b200/csrc/engine.cu: make_units) through the
+host-only C-ABI door mixdir_b200_unit_plan: the packed codes, the unit table T2 and the
+marginalisation of the unit statistics must reproduce the per-feature gather
+(src/mixdir_impl.cpp:77-82) and the per-feature M-step sums (R/mixdir_vi.R:85-91) exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mixdir_b200 import _capi
+
+
+def unit_plan(ncat, m):
+    L = _capi.lib()
+    ncat = np.ascontiguousarray(ncat, dtype=np.int32)
+    J = ncat.size
+    U, NR2 = C.c_int(), C.c_int()
+    ip = C.POINTER(C.c_int)
+    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, C.byref(U), C.byref(NR2), None, None,
+                                 None, None)
+    if st != 0:
+        return None
+    NR = int((ncat + 1).sum())
+    desc = np.zeros((U.value, 4), dtype=np.int32)
+    gbase = np.zeros(U.value, dtype=np.int32)
+    t2src = np.full((NR2.value, 2), -1, dtype=np.int32)
+    marg = np.zeros((NR, 4), dtype=np.int32)
+    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, C.byref(U), C.byref(NR2),
+                                 desc.ctypes.data, gbase.ctypes.data, t2src.ctypes.data, marg.ctypes.data)
+    assert st == 0
+    return dict(U=U.value, NR2=NR2.value, desc=desc, gbase=gbase, t2src=t2src, marg=marg)
+
+
+def pack(codes, desc):
+    out = np.zeros((codes.shape[0], desc.shape[0]), dtype=np.int64)
+    for e, (oa, ob, mul, _) in enumerate(desc):
+        if oa < 0:
+            continue
+        out[:, e] = codes[:, oa]
+        if ob >= 0:
+            out[:, e] = out[:, e] * mul + codes[:, ob]
+    return out
+
+
+@pytest.mark.parametrize("ncat,m", [
+    ([16, 12, 8, 4, 2, 10] * 3, 9), ([16, 12, 8, 4, 2, 10] * 3, 4), ([2, 3, 4, 5, 6], 2),
+    ([10] * 7, 3), ([1, 1, 1], 1), ([15, 15, 3], 1), ([120, 1, 1, 100], 2)])
+def test_unit_plan_reproduces_gather_and_scatter(ncat, m):
+    rng = np.random.default_rng(7)
+    ncat = np.asarray(ncat)
+    J, N, K = ncat.size, 400, 3
+    up = unit_plan(ncat, m)
+    assert up is not None
+    rowoff = np.concatenate([[0], np.cumsum(ncat + 1)[:-1]])
+    NR = int((ncat + 1).sum())
+    codes = np.stack([rng.integers(0, c + 1, size=N) for c in ncat], axis=1)  # 0 = NA
+    u = pack(codes, up["desc"])
+    assert up["U"] % 4 == 0 and u.max() <= 255
+    n_real = int((up["desc"][:, 0] >= 0).sum())
+    assert n_real == J - m and int((up["desc"][:, 1] >= 0).sum()) == m
+    # every feature appears exactly once
+    used = sorted([int(d[0]) for d in up["desc"] if d[0] >= 0] + [int(d[1]) for d in up["desc"] if d[1] >= 0])
+    assert used == list(range(J))
+    # gather: sum over elements of T2[gbase + u] == sum over features of T[rowoff + x]
+    T = rng.normal(size=(NR, K))
+    T[rowoff] = 0.0  # NA rows
+    src = up["t2src"]
+    T2 = T[src[:, 0]] + np.where(src[:, 1:2] >= 0, T[np.maximum(src[:, 1], 0)], 0.0)
+    g2 = up["gbase"][None, :] + u
+    real = up["desc"][:, 0] >= 0
+    assert g2.max() < up["NR2"]
+    lhs = T2[g2[:, real]].sum(axis=1)
+    rhs = T[rowoff[None, :] + codes].sum(axis=1)
+    np.testing.assert_allclose(lhs, rhs, rtol=0, atol=1e-12)
+    # padding elements point at a row whose T2 is zero
+    assert np.all(T2[g2[:, ~real]] == 0.0)
+    # scatter: unit statistics marginalised by marg == feature statistics
+    z = rng.random(size=(N, K))
+    S2 = np.zeros((up["NR2"], K))
+    for e in range(up["U"]):
+        np.add.at(S2, g2[:, e], z)
+    S = np.zeros((NR, K))
+    for j in range(J):
+        np.add.at(S, rowoff[j] + codes[:, j], z)
+    for g in range(NR):
+        start, stride, count, _ = up["marg"][g]
+        if g in set(rowoff.tolist()):
+            assert count == 0  # NA rows are never read (na.rm, R/mixdir_vi.R:88)
+            continue
+        got = S2[start + stride * np.arange(count)].sum(axis=0)
+        np.testing.assert_allclose(got, S[g], rtol=1e-12, atol=1e-12)
+
+
+def test_unit_plan_rejects_pairs_that_do_not_fit_a_byte():
+    assert unit_plan([16, 16], 1) is None      # 17 * 17 = 289 codes
+    assert unit_plan([15, 15], 1) is not None  # 16 * 16 = 256
+    assert unit_plan([3, 3, 3], 2) is None     # more pairs than features allow
+    ident = unit_plan([3, 4, 5], 0)
+    assert ident["NR2"] == 15 and ident["U"] == 4  # identity: padded features, feature tables
