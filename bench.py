@@ -339,9 +339,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (int(traffic["dram_bytes_per_row"] * N) if traffic and
-                                 tm["engine"] == 2 and J == 60 and K == 32 else None),
+                                 tm["engine"] == traffic.get("engine", 2) and J == 60 and K == 32
+                                 else None),
                      "traffic_source": (traffic or {}).get("source"),
-                     "kernel": "k_em_fused" if tm["engine"] == 2 else "k_em_generic",
+                     "kernel": {2: "k_em_fused", 3: "k_em_bucket", 4: "k_em_units"}.get(tm["engine"],
+                                                                                       "k_em_generic"),
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,
                      "kernel_share_of_step": em_ms / loop_ms,
@@ -355,7 +357,8 @@ def run_ours(args):
         "clocks": clocks,
         "engine": {"engine": tm["engine"], "classes_per_cta": tm["classes_per_cta"],
                    "cluster_size": tm["cluster_size"], "grid_ctas": tm["grid_ctas"],
-                   "smem_bytes": tm["smem_bytes"]},
+                   "smem_bytes": tm["smem_bytes"], "unit_elements": tm["unit_elements"],
+                   "feature_pairs": tm["unit_pairs"], "unit_table_rows": tm["unit_table_rows"]},
         "final_pass_ms": predict_ms,
         "elbo_last": float(res["convergence"][-1]),
         "wall_ms_per_step": (t1 - t0) * 1e3 / args.steps,

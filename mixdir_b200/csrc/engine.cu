@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "bucket.cuh"
+#include "units.cuh"
 #include "predict.cuh"
 
 using namespace mxd;
@@ -127,12 +128,18 @@ struct UnitPlan {
   std::vector<int> gbase;      // [U] first unit-table row of element e
   std::vector<int2> t2src;     // [NR2] feature-table rows a unit row is the sum of
   std::vector<MargDesc> marg;  // [NR]  unit rows a feature-table row collects
+  // engine 4 (k_em_units): shared-memory placement, element e at bank position e mod Q
+  int Q = 1, srows = 0;
+  std::vector<int> erows;      // [U] table rows of element e (0: padding)
+  std::vector<int> slot;       // [NR2] unit-table row -> shared-memory slot (row * Q + position)
+  std::vector<int> eoff_rot;   // [4][U] byte offsets, rotated (units.cuh)
 };
 
 struct Plan {
   int engine = 0;  // 1 generic, 2 fused
   int KP = 0;
   int KC = 0, P = 1, RG = 8, W = 0;
+  int FPG = 4;  // engine 4: elements per M-step rotation group
   int n_clusters = 0;
   size_t smem = 0;
   int R = 0;  // rows per tile
@@ -167,6 +174,8 @@ struct Shard {
   int* d_ugbase = nullptr;
   int2* d_t2src = nullptr;
   MargDesc* d_marg = nullptr;
+  int* d_slot = nullptr;           // engine 4: unit-table row -> shared-memory slot
+  int* d_eoff = nullptr;           // engine 4: rotated element offsets
   uint8_t* d_ucodes = nullptr;     // [n_rows + kRowPad][WPRu] words (null: identity plan)
   int64_t packed_rows = 0;         // rows of d_ucodes already packed
   double* d_T2 = nullptr;          // [NR2][KP] (workspace)
@@ -369,6 +378,7 @@ static void free_shard(Shard& s) {
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
   dfree(s.d_ragoff); dfree(s.d_na_row); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
+  dfree(s.d_slot); dfree(s.d_eoff);
   s.unit_valid = false;
   if (s.copy_stream) {
     cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
@@ -792,7 +802,7 @@ extern "C" size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n
   return s * (size_t)n_latent;
 }
 extern "C" int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine) {
-  if (!h || engine < 0 || engine > 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (!h || engine < 0 || engine > 4) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
   h->engine_pref = engine;
   return MIXDIR_B200_OK;
 }
@@ -813,6 +823,7 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 // ---------------------------------------------------------------------------
 typedef void (*fused_fn)(FusedArgs);
 typedef void (*bucket_fn)(BucketArgs);
+typedef void (*units_fn)(UnitArgs);
 
 static fused_fn pick_fused(int KC, int CB, int RG) {
 #define PICK(kc, cb, rg) \
@@ -839,7 +850,9 @@ static bucket_fn pick_bucket(int KC, int CB, int RG) {
   return nullptr;
 }
 
+static units_fn pick_units(int KC, int RG, int FPG);
 static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
+  if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG);
   return p.engine == 3 ? (const void*)pick_bucket(p.KC, h->CB, p.RG)
                        : (const void*)pick_fused(p.KC, h->CB, p.RG);
 }
@@ -896,12 +909,13 @@ static void identity_units(const mixdir_b200_handle* h, UnitPlan* up) {
 // categories are paired smallest-with-largest, which minimises the added table rows
 // sum (C_a+1)(C_b+1) for that many pairs; every pair code must still fit a byte.
 // Returns false if some pair would need more than 256 codes.
-static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up) {
+static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool always_packed = false) {
   const int J = h->J;
-  if (m <= 0) {
+  if (m <= 0 && !always_packed) {
     identity_units(h, up);
     return true;
   }
+  if (m < 0) m = 0;
   if (h->CB != 1 || 2 * m > J) return false;
   std::vector<int> order(J);
   for (int j = 0; j < J; j++) order[j] = j;
@@ -925,6 +939,7 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up) {
     if (b < 0) {
       up->desc.push_back(UnitDesc{j, -1, 1, 0});
       up->gbase.push_back(nr2);
+      up->erows.push_back(Ca + 1);
       for (int c = 0; c <= Ca; c++) up->t2src.push_back(make_int2(h->rowoff[j] + c, -1));
       for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c, 0, 1, 0};
       nr2 += Ca + 1;
@@ -932,6 +947,7 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up) {
       const int Cb = h->ncat[b], mul = Cb + 1;
       up->desc.push_back(UnitDesc{j, b, mul, 0});
       up->gbase.push_back(nr2);
+      up->erows.push_back((Ca + 1) * mul);
       for (int ca = 0; ca <= Ca; ca++)
         for (int cb = 0; cb <= Cb; cb++)
           up->t2src.push_back(make_int2(h->rowoff[j] + ca, h->rowoff[b] + cb));
@@ -944,6 +960,7 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up) {
   while (up->desc.size() % 4) {  // padding elements: code 0 -> the all-NA row of element 0 (scratch)
     up->desc.push_back(UnitDesc{-1, -1, 1, 0});
     up->gbase.push_back(up->gbase[0]);
+    up->erows.push_back(0);
   }
   up->U = (int)up->desc.size();
   up->WPRu = up->U / 4;
@@ -966,6 +983,136 @@ extern "C" int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pair
   if (t2src && !up.identity) memcpy(t2src, up.t2src.data(), up.t2src.size() * sizeof(int2));
   if (marg) memcpy(marg, up.marg.data(), up.marg.size() * sizeof(MargDesc));
   return MIXDIR_B200_OK;
+}
+
+// engine 4 placement: element e sits at bank position e mod Q of the shared-memory table rows
+// (units.cuh).  Re-orders the elements so that the Q stacks are equally high, row 0 of every
+// stack is the zero / scratch row of the padding elements.
+static void layout_units(UnitPlan* up, int KC) {
+  const int Q = KC >= 16 ? 1 : 16 / KC;
+  const int U = up->U, cap = U / Q;
+  std::vector<int> real;
+  for (int e = 0; e < U; e++)
+    if (up->desc[e].off_a >= 0) real.push_back(e);
+  std::stable_sort(real.begin(), real.end(), [&](int a, int b) { return up->erows[a] > up->erows[b]; });
+  std::vector<int> stack(Q, 1), cnt(Q, 0);
+  std::vector<std::vector<std::pair<int, int>>> members(Q);  // (old element, first row in its stack)
+  for (int e : real) {
+    int q = -1;
+    for (int c = 0; c < Q; c++)
+      if (cnt[c] < cap && (q < 0 || stack[c] < stack[q])) q = c;
+    members[q].push_back({e, stack[q]});
+    stack[q] += up->erows[e];
+    cnt[q]++;
+  }
+  std::vector<UnitDesc> desc(U, UnitDesc{-1, -1, 1, 0});
+  std::vector<int> gbase(U, 0), erows(U, 0), eoff(U, 0);
+  up->slot.assign(up->NR2, 0);
+  for (int q = 0; q < Q; q++) {
+    for (int i = 0; i < cap; i++) {
+      const int e = i * Q + q;
+      if (i < (int)members[q].size()) {
+        const int old = members[q][i].first, row0 = members[q][i].second;
+        desc[e] = up->desc[old];
+        gbase[e] = up->gbase[old];
+        erows[e] = up->erows[old];
+        eoff[e] = (row0 * Q + q) * KC * 8;
+        for (int c = 0; c < erows[e]; c++) up->slot[gbase[e] + c] = (row0 + c) * Q + q;
+      } else {
+        eoff[e] = q * KC * 8;  // padding element: code 0 -> row 0 of its position
+      }
+    }
+  }
+  up->desc = desc;
+  up->gbase = gbase;
+  up->erows = erows;
+  up->Q = Q;
+  up->srows = *std::max_element(stack.begin(), stack.end());
+  up->eoff_rot.assign((size_t)4 * U, 0);
+  for (int r = 0; r < 4; r++)
+    for (int e = 0; e < U; e++) up->eoff_rot[(size_t)r * U + e] = eoff[(e & ~3) | ((e + r) & 3)];
+}
+
+static units_fn pick_units(int KC, int RG, int FPG) {
+#define PICK(kc, rg, fpg) \
+  if (KC == kc && RG == rg && FPG == fpg) return k_em_units<kc, rg, fpg>;
+  PICK(32, 8, 2) PICK(32, 4, 2) PICK(32, 2, 2) PICK(32, 8, 4) PICK(32, 4, 4) PICK(32, 2, 4)
+  PICK(16, 8, 2) PICK(16, 4, 2) PICK(16, 2, 2) PICK(16, 8, 4) PICK(16, 4, 4) PICK(16, 2, 4)
+  PICK(8, 8, 4) PICK(8, 4, 4) PICK(8, 2, 4)
+#undef PICK
+  return nullptr;
+}
+
+// engine 4: k_em_units.  Search (KC, RG, pairs) for the cheapest plan that fits shared memory.
+// MIXDIR_B200_FORCE_PLAN="KC,RG,pairs" (tuning aid) restricts the search; -1 leaves a field free.
+static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+  if (h->CB != 1) return false;
+  int fKC = -1, fRG = -1, fM = -1;
+  if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN")) sscanf(f, "%d,%d,%d", &fKC, &fRG, &fM);
+  Plan best;
+  double best_cost = 1e300;
+  const int kcs[3] = {32, 16, 8};
+  const int rgs[3] = {8, 4, 2};
+  for (int KC : kcs) {
+    if (fKC > 0 && KC != fKC) continue;
+    const int RPW = 32 / KC;
+    const int P = (K + KC - 1) / KC;
+    if (P > 8) continue;
+    for (int RG : rgs) {
+      if (fRG > 0 && RG != fRG) continue;
+      if (RG * RPW > 32) continue;
+      UnitPlan up;
+      Plan c;
+      bool found = false;
+      auto shape = [&](UnitPlan& u) -> size_t {
+        layout_units(&u, KC);
+        c.FPG = RPW > 2 ? 4 : (u.U / 4 >= 16 ? 4 : 2);
+        c.W = std::min(16, u.U / c.FPG);
+        while (c.W > 1 && ((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) c.W--;
+        if (((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) return (size_t)-1;
+        return UnitSmem(u.srows, KC, c.W, RG, u.WPRu, P).total;
+      };
+      const int m_hi = fM >= 0 ? std::min(fM, h->J / 2) : (h->pairing ? h->J / 2 : 0);
+      for (int m = m_hi; m >= 0; m--) {
+        if (!make_units(h, m, &up, true)) continue;
+        size_t tot = shape(up);
+        if (tot > (size_t)s.smem_optin) continue;
+        // fewer pairs that still give the same number of code words per row: smaller tables
+        const int m_min = std::max(0, h->J - 4 * up.WPRu);
+        if (m_min < m && fM < 0) {
+          UnitPlan up2;
+          if (make_units(h, m_min, &up2, true) && shape(up2) <= (size_t)s.smem_optin) up = up2;
+          tot = shape(up);
+        }
+        c.smem = tot;
+        found = true;
+        break;
+      }
+      if (!found) continue;
+      c.engine = 4; c.KC = KC; c.P = P; c.RG = RG; c.KP = P * KC;
+      c.R = c.W * RG * RPW;
+      c.up = up;
+      if (!pick_units(KC, RG, c.FPG)) continue;
+      c.n_clusters = plan_occupancy(h, s, c);
+      if (c.n_clusters < 1) continue;
+      // cost model (shared-memory wavefronts per row over all CTAs of a cluster, per SM in use):
+      // 6 wavefronts per element and 256 bytes of classes, a per-row term every CTA repeats
+      // (code words, soft-max, exchange), and per-tile barriers spread over the tile's rows
+      const double used = std::min(1.0, (double)c.n_clusters * P / s.sm_count);
+      const int G = up.U / c.FPG;
+      const double per_row = P * (up.U * 6.0 + 60.0) / RPW;
+      const double per_tile = P * (G * 60.0 + 1500.0) / c.R;
+      const double starve = c.W >= 12 ? 1.0 : 1.0 + 0.03 * (12 - c.W);  // few warps hide less latency
+      const double cost = (per_row + per_tile) * starve / used;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = c;
+      }
+    }
+  }
+  if (best.engine != 4) return false;
+  *out = best;
+  return true;
 }
 
 // engine 2: k_em_fused (row-owned M-step, read-modify-write per row and unit)
@@ -1077,6 +1224,10 @@ static bool plan_bucket(const mixdir_b200_handle* h, const Shard& s, int K, Plan
 // measured slower (profiles/README.md), so it is only a fallback in automatic mode.
 static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
   const int pref = h->engine_pref;
+  if ((pref == 0 || pref == 4) && plan_units(h, s, K, out)) return MIXDIR_B200_OK;
+  if (pref == 4)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "unit kernel does not fit this problem shape (K, sum C_j) "
+                                          "or the codes are 2 bytes wide");
   if ((pref == 0 || pref == 2) && plan_fused(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 2)
     return fail(MIXDIR_B200_BAD_ARGUMENT, "fused kernel does not fit this problem shape (K, sum C_j)");
@@ -1186,7 +1337,8 @@ static int upload_ragoff(mixdir_b200_handle* h, Shard& s, int K) {
 static size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
 static size_t unit_stage_bytes(const UnitPlan& up) {
   return pad8(up.desc.size() * sizeof(UnitDesc)) + pad8(up.gbase.size() * sizeof(int)) +
-         pad8(up.t2src.size() * sizeof(int2)) + pad8(up.marg.size() * sizeof(MargDesc)) + 4 * 64;
+         pad8(up.t2src.size() * sizeof(int2)) + pad8(up.marg.size() * sizeof(MargDesc)) +
+         pad8(up.slot.size() * sizeof(int)) + pad8(up.eoff_rot.size() * sizeof(int)) + 8 * 64;
 }
 
 template <typename T>
@@ -1203,11 +1355,15 @@ static int send_vec(Shard& s, T** dptr, const std::vector<T>& vec) {
 static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
   const UnitPlan& up = pl.up;
   CU_TRY(cudaSetDevice(s.device));
-  if (s.unit_valid && s.unit_sig.size() == up.desc.size() &&
-      memcmp(s.unit_sig.data(), up.desc.data(), up.desc.size() * sizeof(UnitDesc)) == 0)
+  std::vector<UnitDesc> sig = up.desc;  // element order + what the placement depends on
+  sig.push_back(UnitDesc{pl.engine, pl.KC, up.Q, up.srows});
+  sig.push_back(UnitDesc{pl.R, pl.RG, pl.W, pl.FPG});
+  if (s.unit_valid && s.unit_sig.size() == sig.size() &&
+      memcmp(s.unit_sig.data(), sig.data(), sig.size() * sizeof(UnitDesc)) == 0)
     return MIXDIR_B200_OK;
   s.unit_valid = false;
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
+  dfree(s.d_slot); dfree(s.d_eoff);
   s.packed_rows = 0;
   RET_IF(send_vec(s, &s.d_udesc, up.desc));
   RET_IF(send_vec(s, &s.d_ugbase, up.gbase));
@@ -1215,10 +1371,18 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
   if (!up.identity) {
     RET_IF(send_vec(s, &s.d_t2src, up.t2src));
     const size_t rowb = (size_t)up.WPRu * 4;
-    RET_IF(dalloc(&s.d_ucodes, (size_t)(s.n_rows + kRowPad) * rowb));
-    CU_TRY(cudaMemsetAsync(s.d_ucodes + (size_t)s.n_rows * rowb, 0, (size_t)kRowPad * rowb, s.stream));
+    // engine 4 stores the packed codes tile by tile ([tile][word][row in tile]): whole tiles,
+    // the tail of the last one zeroed; engine 2 row-major with kRowPad zero rows behind
+    const int64_t R = pl.engine == 4 ? pl.R : 1;
+    const int64_t full = s.n_rows / R * R, rows_alloc = (s.n_rows + R - 1) / R * R + kRowPad;
+    RET_IF(dalloc(&s.d_ucodes, (size_t)rows_alloc * rowb));
+    CU_TRY(cudaMemsetAsync(s.d_ucodes + (size_t)full * rowb, 0, (size_t)(rows_alloc - full) * rowb, s.stream));
   }
-  s.unit_sig = up.desc;
+  if (pl.engine == 4) {
+    RET_IF(send_vec(s, &s.d_slot, up.slot));
+    RET_IF(send_vec(s, &s.d_eoff, up.eoff_rot));
+  }
+  s.unit_sig = sig;
   s.unit_valid = true;
   return MIXDIR_B200_OK;
 }
@@ -1230,7 +1394,7 @@ static int pack_units(mixdir_b200_handle* h, Shard& s, const Plan& pl, int64_t u
   const int WPRu = pl.up.WPRu;
   const int grid = (int)std::min<int64_t>((int64_t)s.sm_count * 16, (nr * WPRu + 255) / 256);
   k_pack_units<<<grid, 256, 0, s.stream>>>(s.d_codes + (size_t)r0 * h->row_bytes, h->row_bytes, nr,
-                                           s.d_udesc, WPRu,
+                                           s.d_udesc, WPRu, pl.engine == 4 ? pl.R : 0,
                                            reinterpret_cast<uint32_t*>(s.d_ucodes) + (size_t)r0 * WPRu);
   CU_TRY(cudaGetLastError());
   s.packed_rows = upto;
@@ -1329,7 +1493,29 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      if (pl.engine == 3) {
+      if (pl.engine == 4) {
+        UnitArgs u;
+        u.codes = a.codes;
+        u.n_rows = nr;
+        u.n_tiles = n_tiles;
+        u.WPR = up.WPRu;
+        u.NR2 = up.NR2;
+        u.srows = up.srows;
+        u.K = K;
+        u.KP = pl.KP;
+        u.P = pl.P;
+        u.eoff_rot = s.d_eoff;
+        u.slot_of_row = s.d_slot;
+        u.T2 = s.d_T2;
+        u.logprior = s.d_logprior;
+        u.Spart = s.d_Spart;
+        u.cspart = s.d_cspart;
+        u.Hpart = s.d_Hpart;
+        u.underflow = s.d_underflow;
+        u.accumulate = chunked ? 1 : 0;
+        u.bad = &s.d_scan->bad;
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_units(pl.KC, pl.RG, pl.FPG), u));
+      } else if (pl.engine == 3) {
         BucketArgs b;
         b.f = a;
         b.J = h->J;
@@ -1690,7 +1876,7 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   if (!h || !log_prior || !table) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
-  if (engine < 0 || engine > 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (engine < 0 || engine > 4) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
   RET_IF(resolve_scan(h));
   const int keep = h->engine_pref;
   if (engine) h->engine_pref = engine;

@@ -578,14 +578,27 @@ struct UnitDesc {
   int pad;
 };
 
-// raw row-major codes (1 byte per cell) -> unit codes, WPRu 32-bit words per row
+// raw row-major codes (1 byte per cell) -> unit codes, WPRu 32-bit words per row.
+// R == 0: row-major output [row][WPRu]; R > 0: tile-transposed output [row / R][WPRu][row % R]
+// (k_em_units); `out` and the row numbering start at a tile boundary.
 __global__ void k_pack_units(const uint8_t* __restrict__ raw, int row_bytes, int64_t n_rows,
-                             const UnitDesc* __restrict__ units, int WPRu, uint32_t* __restrict__ out) {
-  const int64_t total = n_rows * WPRu;
+                             const UnitDesc* __restrict__ units, int WPRu, int R,
+                             uint32_t* __restrict__ out) {
+  const int64_t total = (R > 0 ? (n_rows + R - 1) / R * R : n_rows) * WPRu;
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
        w += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = w / WPRu;
-    const int col = (int)(w - row * WPRu);
+    int64_t row;
+    int col;
+    if (R > 0) {  // consecutive threads -> consecutive rows of one word column (coalesced stores)
+      const int64_t tile = w / ((int64_t)R * WPRu);
+      const int rem = (int)(w - tile * (int64_t)R * WPRu);
+      col = rem / R;
+      row = tile * R + (rem - col * R);
+      if (row >= n_rows) continue;  // tail of the last tile: stays zero
+    } else {
+      row = w / WPRu;
+      col = (int)(w - row * WPRu);
+    }
     const uint8_t* r = raw + row * row_bytes;
     uint32_t cw = 0;
 #pragma unroll
@@ -602,6 +615,7 @@ __global__ void k_pack_units(const uint8_t* __restrict__ raw, int row_bytes, int
     out[w] = cw;
   }
 }
+static_assert(sizeof(UnitDesc) == 16, "UnitDesc is read as int4");
 
 // unit table from the feature table: T2[g2][k] = T[src.x][k] + T[src.y][k]  (src.y < 0: single)
 __global__ void k_build_T2(const int2* __restrict__ src, int NR2, int KP, const double* __restrict__ T,

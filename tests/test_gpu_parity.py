@@ -33,7 +33,7 @@ def rel(a, b):
     return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300))
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3], ids=["generic", "fused", "bucket"])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4], ids=["generic", "fused", "bucket", "units"])
 @pytest.mark.parametrize("name", FIT_FIXTURES)
 def test_fit_matches_golden(name, engine, mushroom):
     g = load_golden(name)
@@ -68,7 +68,7 @@ def test_fit_matches_golden(name, engine, mushroom):
     assert r["warn_flags"] == int(g["warn_flags"])
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3], ids=["generic", "fused", "bucket"])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4], ids=["generic", "fused", "bucket", "units"])
 @pytest.mark.parametrize("tag", ["k3", "k10"])
 def test_estep_matches_reference_native_functions(tag, engine):
     """kernel zeta / statistics vs the reference's own update_zeta_cpp / update_zeta_dp_cpp /
@@ -119,7 +119,7 @@ def test_fit_live_oracle_random_shapes():
         z0 = synth.zeta_init(case, N, K)
         p0 = synth.phi_init(case, ncat, K)
         ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, dp, 1.0, 1.0, 0.1, 25, 1e-3, z0, p0)
-        for engine in (1, 2, 3):
+        for engine in (1, 2, 3, 4):
             with Engine(codes, ncat) as eng:
                 eng.set_engine(engine)
                 r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), max_iter=25, epsilon=1e-3,
@@ -173,7 +173,7 @@ def test_underflow_is_an_error(dp):
     codes2, _ = synth.make_codes(1, 64, ncat2, 2)
     p_big = synth.phi_init(1, ncat2, 2).copy()
     p_big[::2] = 1e-300  # psi(1e-300) ~ -1e300: every logit underflows
-    for engine in (2, 3):
+    for engine in (2, 3, 4):
         with Engine(codes2, ncat2) as eng:
             eng.set_engine(engine)
             with pytest.raises(ZetaUnderflow):
@@ -233,12 +233,16 @@ def test_full_size_properties():
     p0 = synth.phi_init(2, pat, K)
     cs0 = np.full(K, N / K)
     outs = {}
-    for engine in (1, 2, 3):
+    for engine in (1, 2, 3, 4):
         with Engine(codes, pat) as eng:
             eng.set_engine(engine)
             outs[engine] = eng.fit(K, cs0, p0, max_iter=4, epsilon=-np.inf, want_class_prob=False)
             outs[engine]["timing"] = eng.timing()
     assert outs[3]["timing"]["engine"] == 3
+    assert outs[4]["timing"]["engine"] == 4 and outs[4]["timing"]["unit_pairs"] > 0
+    assert rel(outs[4]["convergence"], outs[2]["convergence"]) < 1e-11
+    assert np.array_equal(outs[4]["pred_class"], outs[2]["pred_class"])
+    np.testing.assert_allclose(outs[4]["phi"], outs[2]["phi"], rtol=1e-9, atol=1e-9)
     assert rel(outs[3]["convergence"], outs[2]["convergence"]) < 1e-11
     assert np.array_equal(outs[3]["pred_class"], outs[2]["pred_class"])
     np.testing.assert_allclose(outs[3]["phi"], outs[2]["phi"], rtol=1e-9, atol=1e-9)
@@ -276,13 +280,13 @@ def test_cluster_shapes_against_oracle(K, J, dp):
     z0 = synth.zeta_init(3, N, K)
     p0 = synth.phi_init(3, pat, K)
     ref = po.fit(po.codes_to_r_matrix(codes), pat, K, dp, 1.0, 1.0, 0.1, 4, -np.inf, z0, p0)
-    for engine in (0, 1, 2):
+    for engine in (0, 1, 2, 4):
         with Engine(codes, pat) as eng:
             eng.set_engine(engine)
             try:
                 r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), max_iter=4, epsilon=-np.inf)
             except MixdirError as e:
-                if engine == 2 and "does not fit" in str(e):
+                if engine in (2, 4) and "does not fit" in str(e):
                     continue
                 raise
             t = eng.timing()
@@ -305,7 +309,7 @@ def test_recycled_buffers_do_not_leak_stale_codes():
     z0 = synth.zeta_init(3, n, 3)
     p0 = synth.phi_init(3, ncat, 3)
     ref = po.fit(po.codes_to_r_matrix(codes), ncat, 3, 0, 1.0, 1.0, 0.1, 6, -np.inf, z0, p0)
-    for engine in (2, 3, 1):
+    for engine in (2, 3, 1, 4):
         with Engine(codes, ncat) as eng:
             eng.set_engine(engine)
             r = eng.fit(3, z0.sum(axis=0), p0, max_iter=6, epsilon=-np.inf)
@@ -326,20 +330,21 @@ def test_feature_pair_units_against_oracle(K, J, p_na):
     p0 = synth.phi_init(5, pat, K)
     ref = po.fit(po.codes_to_r_matrix(codes), pat, K, 0, 1.0, 1.0, 0.1, 5, -np.inf, z0, p0)
     pairs = {}
-    for on in (True, False):
+    for engine, on in ((2, True), (2, False), (4, True), (4, False)):
         with Engine(codes, pat) as eng:
-            eng.set_engine(2)
+            eng.set_engine(engine)
             eng.set_pairing(on)
             r = eng.fit(K, z0.sum(axis=0), p0, max_iter=5, epsilon=-np.inf)
             t = eng.timing()
             # a second fit on the same handle reuses the packed unit codes
             r2 = eng.fit(K, z0.sum(axis=0), p0, max_iter=5, epsilon=-np.inf)
-        pairs[on] = t["unit_pairs"]
+        assert t["engine"] == engine
+        pairs[(engine, on)] = t["unit_pairs"]
         assert np.array_equal(r["convergence"], r2["convergence"])
         assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
         assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
         assert np.array_equal(r["pred_class"], ref["pred_class"])
         np.testing.assert_allclose(r["phi"], ref["phi"], rtol=1e-10, atol=1e-10)
-    assert pairs[False] == 0
+    assert pairs[(2, False)] == 0 and pairs[(4, False)] == 0
     if (J + 3) // 4 > (J - J // 2 + 3) // 4:  # pairing is used when it saves code words per row
-        assert pairs[True] > 0, pairs
+        assert pairs[(2, True)] > 0 and pairs[(4, True)] > 0, pairs
