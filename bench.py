@@ -58,9 +58,9 @@ def hbm_peak():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu capture, or None."""
+    """dram bytes per row of the hot kernel from the committed ncu capture, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "em_fused_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "em_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return None
@@ -347,8 +347,9 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,
                      "kernel_share_of_step": em_ms / loop_ms,
-                     "note": "shared-memory bound, not HBM bound: see DESIGN.md (K gathers + K "
-                             "read-modify-writes of fp64 per code byte)"},
+                     "note": "shared-memory bound, not HBM bound: see DESIGN.md 4.1 (per code, K fp64 "
+                             "table gathers + K fp64 histogram read-modify-writes; the shared-memory "
+                             "pipe runs at 80 % of its wavefront peak, profiles/README.md)"},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": f"{args.cpu_rows} rows x {J} features, K={K}, 2 iterations "
                                    f"({cpu_dt:.2f} s/iter), same generator as the GPU workload; "

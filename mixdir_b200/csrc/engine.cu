@@ -1044,11 +1044,13 @@ static units_fn pick_units(int KC, int RG, int FPG) {
 }
 
 // engine 4: k_em_units.  Search (KC, RG, pairs) for the cheapest plan that fits shared memory.
-// MIXDIR_B200_FORCE_PLAN="KC,RG,pairs" (tuning aid) restricts the search; -1 leaves a field free.
+// MIXDIR_B200_FORCE_PLAN="KC,RG,pairs[,FPG[,W]]" (tuning aid, tools/sweep_plans.py) restricts the
+// search; -1 leaves a field free.
 static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
   if (h->CB != 1) return false;
-  int fKC = -1, fRG = -1, fM = -1;
-  if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN")) sscanf(f, "%d,%d,%d", &fKC, &fRG, &fM);
+  int fKC = -1, fRG = -1, fM = -1, fFPG = -1, fW = -1;
+  if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN"))
+    sscanf(f, "%d,%d,%d,%d,%d", &fKC, &fRG, &fM, &fFPG, &fW);
   Plan best;
   double best_cost = 1e300;
   const int kcs[3] = {32, 16, 8};
@@ -1067,23 +1069,22 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       auto shape = [&](UnitPlan& u) -> size_t {
         layout_units(&u, KC);
         c.FPG = RPW > 2 ? 4 : (u.U / 4 >= 16 ? 4 : 2);
+        if (fFPG > 0 && fFPG >= RPW) c.FPG = fFPG;
         c.W = std::min(16, u.U / c.FPG);
+        if (fW > 0) c.W = std::min(c.W, fW);
         while (c.W > 1 && ((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) c.W--;
         if (((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) return (size_t)-1;
         return UnitSmem(u.srows, KC, c.W, RG, u.WPRu, P).total;
       };
+      // Only the number of code words per row (4 elements each) matters: for every word count,
+      // fewest first, try the smallest number of pairs that reaches it.
       const int m_hi = fM >= 0 ? std::min(fM, h->J / 2) : (h->pairing ? h->J / 2 : 0);
-      for (int m = m_hi; m >= 0; m--) {
-        if (!make_units(h, m, &up, true)) continue;
-        size_t tot = shape(up);
+      const int w_lo = (h->J - m_hi + 3) / 4, w_hi = (h->J + 3) / 4;
+      for (int w = w_lo; w <= w_hi; w++) {
+        const int m = fM >= 0 ? m_hi : std::max(0, h->J - 4 * w);
+        if (m > m_hi || !make_units(h, m, &up, true)) continue;
+        const size_t tot = shape(up);
         if (tot > (size_t)s.smem_optin) continue;
-        // fewer pairs that still give the same number of code words per row: smaller tables
-        const int m_min = std::max(0, h->J - 4 * up.WPRu);
-        if (m_min < m && fM < 0) {
-          UnitPlan up2;
-          if (make_units(h, m_min, &up2, true) && shape(up2) <= (size_t)s.smem_optin) up = up2;
-          tot = shape(up);
-        }
         c.smem = tot;
         found = true;
         break;
@@ -1139,18 +1140,14 @@ static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       while (((size_t)W * RG * RPW * u.WPRu) % 4 != 0 && RG < 8) RG *= 2;
       return FusedSmem(u.NR2, KC, W, RG, u.WPRu, FPW, P);
     };
-    for (int m = (h->pairing && h->CB == 1) ? h->J / 2 : 0; m >= 0; m--) {
-      if (!make_units(h, m, &up)) continue;
+    const int m_hi = (h->pairing && h->CB == 1) ? h->J / 2 : 0;
+    const int w_lo = (h->J - m_hi + 3) / 4, w_hi = (h->J + 3) / 4;
+    for (int w = m_hi ? w_lo : w_hi; w <= w_hi; w++) {
+      // smallest number of pairs that gives w code words per row (none: the raw code matrix)
+      const int m = m_hi ? std::max(0, h->J - 4 * w) : 0;
+      if (m > m_hi || !make_units(h, m, &up)) continue;
       FusedSmem L = shape(up);
       if (L.total > (size_t)s.smem_optin) continue;
-      // fewer pairs that still give the same number of code words per row: smaller tables
-      const int m_min = std::max(0, h->J - 4 * up.WPRu);
-      if (m > 0 && m_min < m && make_units(h, m_min, &up)) {
-        L = shape(up);
-      } else if (m > 0) {
-        make_units(h, m, &up);
-        L = shape(up);
-      }
       smem = L.total;
       found = true;
       break;

@@ -93,7 +93,8 @@ __device__ __forceinline__ void load_code_words(const uint32_t* p, uint32_t* out
 template <int KC, int RG, int FPG>
 __global__ void __launch_bounds__(512, 1) k_em_units(UnitArgs a) {
   constexpr int RPW = 32 / KC;                       // rows per warp instruction ("slots")
-  constexpr int Q = KC >= 16 ? 1 : 16 / KC;          // table rows side by side in a 128-byte row
+  // (Q = 16/KC table rows sit side by side in a 128-byte shared-memory row; the placement is
+  //  done on the host -- engine.cu: layout_units -- and arrives through eoff_rot / slot_of_row)
   constexpr int RW = RG * RPW;                       // rows per warp per tile
   constexpr uint32_t RS = KC * 8 > 128 ? KC * 8 : 128;  // bytes per shared-memory table row
   static_assert(RPW <= FPG, "slots of a warp must work on distinct elements of a group");
