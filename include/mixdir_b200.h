@@ -180,7 +180,8 @@ int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const double* lambd
  *   table          ragged T[j][k][r] = psi(phi_jkr) - psi(sum_r phi_jkr)
  *   S (ragged), colsum[K], entropy, underflow: the statistics buffer
  *   zeta (nullable) n_rows x K column-major normalised responsibilities
- *   engine         0 = automatic, 1 = generic kernel, 2 = fused kernel, 3 = bucketed fused kernel */
+ *   engine         0 = automatic, 1 = generic kernel, 2 = fused kernel, 3 = bucketed fused kernel,
+ *                  4 = unit kernel (1-byte codes) */
 int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const double* log_prior,
                       const double* table, int engine, double* S, double* colsum,
                       double* entropy, int* underflow, double* zeta);
@@ -192,7 +193,8 @@ typedef struct mixdir_b200_timing {
   int iterations;       /* iterations executed */
   int em_launches;      /* E+M kernel launches in the loop */
   int total_launches;   /* all kernel launches of the library inside the loop (per device) */
-  int engine;           /* 1 generic, 2 fused (k_em_fused), 3 bucketed fused (k_em_bucket) */
+  int engine;           /* 1 generic, 2 fused (k_em_fused), 3 bucketed fused (k_em_bucket),
+                           4 unit kernel (k_em_units) */
   int classes_per_cta;  /* fused: KC */
   int cluster_size;     /* fused: P */
   int grid_ctas;        /* fused: CTAs launched */
@@ -203,10 +205,11 @@ typedef struct mixdir_b200_timing {
 } mixdir_b200_timing;
 
 int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out);
-/* 0 = automatic (default), 1 = generic kernel only, 2 = fused kernel or fail,
- * 3 = bucketed fused kernel or fail */
+/* 0 = automatic (default: unit kernel for 1-byte codes, else fused, else bucketed, else generic),
+ * 1 = generic kernel only, 2 = fused kernel or fail, 3 = bucketed fused kernel or fail,
+ * 4 = unit kernel or fail */
 int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine);
-/* Feature pairing of the fused kernel (default on): two features share one table gather and one
+/* Feature pairing of the fused and unit kernels (default on): two features share one table gather and one
  * histogram update where shared memory allows.  Results change only by floating-point
  * re-association inside the per-row logit sum (mixdir_impl.cpp:77-82).  0 switches it off. */
 int mixdir_b200_set_pairing(mixdir_b200_handle* h, int on);
