@@ -204,6 +204,22 @@ typedef struct mixdir_b200_timing {
   int unit_table_rows;  /* fused: rows of the unit tables (sum over elements of their codes) */
 } mixdir_b200_timing;
 
+/* Inner loop of find_defining_features() (/root/reference/R/predict.R:266-339; the `vapply` over the
+ * remaining variables at :299-310).  With p = predict(all features of the handle's rows) and, for every
+ * feature i with active[i] != 0, q_i = predict(active features without i) -- both in the arithmetic of
+ * predict_class (R/predict.R:88-103; dropped features and NA cells contribute 1) --
+ *   measure 0 ("JS"):  out[i] = sum_{rows,k} (q (log q - log p) + p (log p - log q)) / 2    (:304)
+ *   measure 1 ("ARI"): out[i] = 1 - adjusted Rand index(which.max q, which.max p)           (:306;
+ *                      the reference calls mcclust::arandi, not vendored: standard Hubert-Arabie form)
+ * out[n_features] is the same quantity for the active set itself (nothing else removed; the final
+ * quality of :326-331); out[i] = NaN for inactive i.  `rows` (optional): 0-based row subsample of the
+ * handle's rows (R: X[subsample, ]), NULL = every row.  One pass over the codes serves all candidates:
+ * the reference makes |active| predict() calls per round.
+ *   lambda         [K]    category_prob  ragged (j,k,r) as returned by fit      out  [n_features + 1] */
+int mixdir_b200_feature_divergence(mixdir_b200_handle* h, int n_latent, const double* lambda,
+                                   const double* category_prob, const unsigned char* active,
+                                   int measure, const int64_t* rows, int64_t n_rows_sub, double* out);
+
 int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out);
 /* 0 = automatic (default: unit kernel for 1-byte codes, else fused, else bucketed, else generic),
  * 1 = generic kernel only, 2 = fused kernel or fail, 3 = bucketed fused kernel or fail,

@@ -1,7 +1,8 @@
 """Python mirror of the reference's user entry points, on top of the CUDA engine.
 
-  mixdir()   <->  /root/reference/R/mixdir.R:79-138
-  predict()  <->  /root/reference/R/predict.R:29-105
+  mixdir()                  <->  /root/reference/R/mixdir.R:79-138
+  predict()                 <->  /root/reference/R/predict.R:29-105
+  find_defining_features()  <->  /root/reference/R/predict.R:266-339
 
 R is not available in this image, so this module plays the role of the R adapter
 (r_adapter/ holds the Rcpp/R sources a maintainer would add):
@@ -107,6 +108,17 @@ def predict(obj, newdata=None):
     class probabilities of new rows under (lambda, category_prob)."""
     if newdata is None:
         return obj["class_prob"]
+    categories = obj["_categories"]
+    codes = _recode_new(obj, newdata)
+    ncat = np.array([len(c) for c in categories], dtype=np.int32)
+    K = len(obj["lambda"])
+    with Engine(codes, ncat) as eng:
+        cp, _ = eng.predict(K, obj["lambda"], obj["_U_flat"], want_pred_class=False)
+    return cp
+
+
+def _recode_new(obj, newdata):
+    """name matching, unseen-level warning and NA handling of predict_class (R/predict.R:64-84)."""
     names, categories = obj["_names"], obj["_categories"]
     nd_names, nd_cols = _as_columns(newdata)
     by_name = dict(zip(nd_names, nd_cols))
@@ -118,8 +130,74 @@ def predict(obj, newdata=None):
         lst = ",".join(f'"{v}"' for v in sorted(vals))
         warnings.warn(f'The new data has a response ({lst}) for category "{col}" which is not in '
                       "category_prob. Handling X[j, i] it as if it was missing.\n")
-    ncat = np.array([len(c) for c in categories], dtype=np.int32)
+    return codes
+
+
+def _r_order(values):
+    """R's order(): ascending, stable, NA/NaN last."""
+    v = np.asarray(values, dtype=float)
+    idx = np.arange(v.size)
+    nan = np.isnan(v)
+    return np.concatenate([idx[~nan][np.argsort(v[~nan], kind="stable")], idx[nan]])
+
+
+def find_defining_features(obj, X, n_features=np.inf, measure="JS", subsample_size=np.inf,
+                           step_size=np.inf, exponential_decay=True, verbose=False, subsample=None,
+                           seed=None, devices=None):
+    """find_defining_features (R/predict.R:266-339): greedy feature elimination by the loss of
+    clustering quality.  Returns dict(features=..., quality=...).  The control flow below is the
+    reference's; each round's |remaining| predict() calls are one device pass
+    (Engine.feature_divergence).  `subsample` (0-based row indices) replaces R's sample(), whose
+    stream is not reproducible outside R."""
+    if measure not in ("JS", "ARI"):  # match.arg
+        raise ValueError("'arg' should be one of \"JS\", \"ARI\"")
+    if exponential_decay is True:
+        exponential_step = 2.0
+    elif isinstance(exponential_decay, (int, float)) and not isinstance(exponential_decay, bool):
+        exponential_step = float(exponential_decay)
+    else:
+        exponential_step = np.nan
+    early_stop = 0 if np.isinf(n_features) else int(n_features)
+    codes = _recode_new(obj, X)
+    names = obj["_names"]
+    J, n = len(names), codes.shape[0]
+    if subsample is None:
+        rng = np.random.default_rng(seed)
+        size = int(min(n, subsample_size))
+        subsample = rng.permutation(n)[:size]  # sample(seq_len(nrow(X)), size=..., replace=FALSE)
+    subsample = np.asarray(subsample, dtype=np.int64)
+    ncat = np.array([len(c) for c in obj["_categories"]], dtype=np.int32)
     K = len(obj["lambda"])
-    with Engine(codes, ncat) as eng:
-        cp, _ = eng.predict(K, obj["lambda"], obj["_U_flat"], want_pred_class=False)
-    return cp
+    remaining = list(range(J))
+    removed, quality = [], []
+    diverg = np.zeros(0)
+    with Engine(codes, ncat, devices=devices) as eng:
+        def divergences(cols):
+            active = np.zeros(J, dtype=np.uint8)
+            active[cols] = 1
+            return eng.feature_divergence(K, obj["lambda"], obj["_U_flat"], active, measure,
+                                          rows=subsample)
+        while len(remaining) > early_stop:
+            diverg = divergences(remaining)[remaining]  # R/predict.R:299-310
+            exp_step = (np.floor(len(remaining) * (1 - 1 / exponential_step))
+                        if exponential_decay else np.inf)
+            last_rm_idx = int(max(min(step_size, exp_step, len(remaining) - early_stop), 1))
+            order = _r_order(diverg)[:last_rm_idx]
+            removed += [remaining[i] for i in order]
+            quality += [float(diverg[i]) for i in order]
+            remaining = [j for j in range(J) if j not in removed]  # setdiff(colnames(X), removed_vars)
+            if verbose:
+                print(f"Remaining variables: {len(remaining)}")
+        if measure == "ARI":
+            quality = [1 - q for q in quality]
+        if not np.isinf(n_features) and n_features != 0:
+            if diverg.size == 0:  # n_features >= ncol(X): the reference stops here as well
+                raise ValueError("object 'diverg' not found")
+            last = divergences(remaining)[J]  # predict with exactly the remaining variables
+            q = float(last) if measure == "JS" else float(1 - last)
+            # "Not perfect order but better than random" (R/predict.R:333)
+            head = -np.asarray(diverg[:len(remaining)], dtype=float)
+            feats = [names[remaining[i]] for i in _r_order(head)]
+            return {"features": feats, "quality": q}
+    feats = [names[j] for j in (removed + remaining)][::-1]
+    return {"features": feats, "quality": quality[::-1]}

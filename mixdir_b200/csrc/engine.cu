@@ -26,6 +26,7 @@
 #include "bucket.cuh"
 #include "units.cuh"
 #include "predict.cuh"
+#include "features.cuh"
 
 using namespace mxd;
 
@@ -1865,6 +1866,137 @@ extern "C" int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const do
     CU_TRY(cudaStreamSynchronize(s.stream));  // lpad is a local
   }
   return run_predict(h, K, pl.KP, class_prob, pred_class);
+}
+
+// adjusted Rand index of a K x K contingency table (Hubert & Arabie; what mcclust::arandi computes)
+static double adjusted_rand(const unsigned long long* c, int K) {
+  auto c2 = [](double x) { return x * (x - 1.0) / 2.0; };
+  std::vector<double> a(K, 0.0), b(K, 0.0);
+  double n = 0, sij = 0;
+  for (int i = 0; i < K; i++)
+    for (int j = 0; j < K; j++) {
+      const double v = (double)c[(size_t)i * K + j];
+      a[i] += v;
+      b[j] += v;
+      n += v;
+      sij += c2(v);
+    }
+  double sa = 0, sb = 0;
+  for (int i = 0; i < K; i++) {
+    sa += c2(a[i]);
+    sb += c2(b[i]);
+  }
+  const double correc = sa * sb / c2(n);
+  return (sij - correc) / (0.5 * sa + 0.5 * sb - correc);
+}
+
+extern "C" int mixdir_b200_feature_divergence(mixdir_b200_handle* h, int n_latent, const double* lambda,
+                                              const double* category_prob,
+                                              const unsigned char* active, int measure,
+                                              const int64_t* rows, int64_t n_rows_sub, double* out) {
+  if (!h || !lambda || !category_prob || !active || !out)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
+  const int K = n_latent, J = h->J;
+  if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  if (measure != 0 && measure != 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "measure must be 0 (JS) or 1 (ARI)");
+  if (rows && n_rows_sub < 0) return fail(MIXDIR_B200_BAD_ARGUMENT, "negative subsample size");
+  if (rows && h->world > 1)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "row subsamples are not supported by multi-process handles");
+  if (rows)
+    for (int64_t i = 0; i < n_rows_sub; i++)
+      if (rows[i] < 0 || rows[i] >= h->n_rows) return fail(MIXDIR_B200_BAD_ARGUMENT, "subsample row out of range");
+  const size_t ncont = (size_t)(J + 1) * K * K;
+  if (measure == 1 && ncont > ((size_t)1 << 27))
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "ARI contingency tables too large ((J+1) * K^2 > 2^27)");
+  RET_IF(resolve_scan(h));
+  Plan pl;
+  pl.engine = 1;
+  pl.KP = (K + 7) & ~7;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  const int jk_grid = (J * K + 127) / 128;
+  std::vector<double> lpad(pl.KP, 0.0);
+  for (int k = 0; k < K; k++) lpad[k] = lambda[k];
+  const size_t nout = (size_t)J + 1;
+  std::vector<void*> bufs(h->shards.size());
+  struct Tmp { unsigned char* act = nullptr; int64_t* rows = nullptr; double* partial = nullptr;
+               double* res = nullptr; unsigned long long* cont = nullptr; };
+  std::vector<Tmp> tmp(h->shards.size());
+  auto cleanup = [&]() {
+    for (auto& t : tmp) { dfree(t.act); dfree(t.rows); dfree(t.partial); dfree(t.res); dfree(t.cont); }
+  };
+  int status = MIXDIR_B200_OK;
+  for (size_t si = 0; si < h->shards.size() && status == MIXDIR_B200_OK; si++) {
+    Shard& s = h->shards[si];
+    Tmp& t = tmp[si];
+    status = [&]() -> int {
+      RET_IF(ensure_workspace(h, s, K, pl, 1));
+      RET_IF(pin_reset(s, (size_t)J * 8 + 4096));
+      RET_IF(upload_ragoff(h, s, K));
+      CU_TRY(cudaMemcpyAsync(s.d_rag_a, category_prob, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+      CU_TRY(cudaMemcpyAsync(s.d_lambda_pad, lpad.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+      ScatterRagArgs ra = {J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_logU, 1, 0.0};
+      k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
+      CU_TRY(cudaGetLastError());
+      // one warp per row; the per-warp accumulators [J+1] live in shared memory
+      int warps = (int)std::min<size_t>(8, (size_t)48 * 1024 / (nout * sizeof(double)));
+      if (warps < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "too many features for feature_divergence (J > 6143)");
+      const int64_t n = rows ? n_rows_sub : s.n_rows;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s.sm_count * 8, (n + warps - 1) / warps));
+      RET_IF(dalloc(&t.act, (size_t)J));
+      RET_IF(dalloc(&t.partial, (size_t)grid * nout));
+      RET_IF(dalloc(&t.res, nout));
+      CU_TRY(cudaMemcpyAsync(t.act, active, J, cudaMemcpyHostToDevice, s.stream));
+      if (rows) {
+        RET_IF(dalloc(&t.rows, (size_t)std::max<int64_t>(n_rows_sub, 1)));
+        CU_TRY(cudaMemcpyAsync(t.rows, rows, n_rows_sub * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+      }
+      if (measure == 1) {
+        RET_IF(dalloc(&t.cont, ncont));
+        CU_TRY(cudaMemsetAsync(t.cont, 0, ncont * sizeof(unsigned long long), s.stream));
+      }
+      FeatureDivArgs a = {s.d_codes, h->row_bytes, s.n_rows, s.row0, t.rows, n_rows_sub, J, K, pl.KP,
+                          s.d_rowoff, s.d_logU, s.d_lambda_pad, t.act, measure, t.partial, t.cont};
+      const size_t smem = (size_t)warps * nout * sizeof(double);
+      if (s.n_rows > 0) {
+        if (h->CB == 1)
+          k_feature_div<1><<<grid, 32 * warps, smem, s.stream>>>(a);
+        else
+          k_feature_div<2><<<grid, 32 * warps, smem, s.stream>>>(a);
+        CU_TRY(cudaGetLastError());
+        k_feature_div_reduce<<<(int)((nout + 127) / 128), 128, 0, s.stream>>>(t.partial, grid, (int)nout, t.res);
+        CU_TRY(cudaGetLastError());
+      } else {
+        CU_TRY(cudaMemsetAsync(t.res, 0, nout * sizeof(double), s.stream));
+      }
+      bufs[si] = measure == 1 ? (void*)t.cont : (void*)t.res;
+      CU_TRY(cudaStreamSynchronize(s.stream));  // lpad / host inputs are read by the copies above
+      return MIXDIR_B200_OK;
+    }();
+  }
+  if (status == MIXDIR_B200_OK)
+    status = measure == 1 ? allreduce(h, bufs, ncont, nccl::kInt64, nccl::kSum)
+                          : allreduce(h, bufs, nout, nccl::kDouble, nccl::kSum);
+  if (status == MIXDIR_B200_OK) {
+    status = [&]() -> int {
+      Shard& s = h->shards[0];
+      CU_TRY(cudaSetDevice(s.device));
+      if (measure == 0) {
+        CU_TRY(cudaMemcpyAsync(out, tmp[0].res, nout * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaStreamSynchronize(s.stream));
+      } else {
+        std::vector<unsigned long long> cont(ncont);
+        CU_TRY(cudaMemcpyAsync(cont.data(), tmp[0].cont, ncont * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaStreamSynchronize(s.stream));
+        for (int i = 0; i <= J; i++) out[i] = 1.0 - adjusted_rand(cont.data() + (size_t)i * K * K, K);
+      }
+      for (int i = 0; i < J; i++)
+        if (!active[i]) out[i] = NAN;
+      return MIXDIR_B200_OK;
+    }();
+  }
+  cleanup();
+  return status;
 }
 
 extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const double* log_prior,

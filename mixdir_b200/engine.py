@@ -221,6 +221,24 @@ class Engine:
         _check(_capi.lib().mixdir_b200_predict(self._h, K, _ptr(lam), _ptr(U), _ptr(cp), _ptr(pc)))
         return cp, pc
 
+    def feature_divergence(self, n_latent, lambda_, category_prob, active, measure="JS", rows=None):
+        """Quality loss per still-active feature if it were removed as well -- the inner loop of
+        find_defining_features (R/predict.R:299-310) -- and, last entry, of the active set itself."""
+        K = int(n_latent)
+        lam = np.ascontiguousarray(lambda_, dtype=np.float64)
+        U = np.ascontiguousarray(category_prob, dtype=np.float64)
+        if lam.size != K or U.size != self.ragged_size(K):
+            raise ValueError("lambda / category_prob have the wrong size")
+        act = np.ascontiguousarray(np.asarray(active).astype(bool), dtype=np.uint8)
+        if act.size != self.n_features:
+            raise ValueError("active must have one flag per feature")
+        m = {"JS": 0, "ARI": 1}[measure]
+        out = np.zeros(self.n_features + 1)
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        _check(_capi.lib().mixdir_b200_feature_divergence(
+            self._h, K, _ptr(lam), _ptr(U), _ptr(act), m, _ptr(r), 0 if r is None else r.size, _ptr(out)))
+        return out
+
     def estep(self, n_latent, log_prior, table, engine=0, want_zeta=False):
         """Unit-test door: one E+M pass with caller tables (see include/mixdir_b200.h)."""
         K = int(n_latent)

@@ -209,3 +209,78 @@ def estep_stats(codes, ncat, K, logprior, T, row0=0, row1=None, want_zeta=False)
                              _d(lp), _d(T), _d(S), _d(cs), C.byref(H), C.byref(uf),
                              _d(zeta) if want_zeta else None)
     return dict(S=S, cs=cs, H=H.value, underflow=uf.value, zeta=zeta)
+
+
+def adjusted_rand(c1, c2):
+    """mcclust::arandi(cl1, cl2, adjust=TRUE) (package not vendored with the reference; the
+    published Hubert-Arabie formula it implements)."""
+    c1 = np.asarray(c1)
+    c2 = np.asarray(c2)
+    _, i1 = np.unique(c1, return_inverse=True)
+    _, i2 = np.unique(c2, return_inverse=True)
+    tab = np.zeros((i1.max() + 1, i2.max() + 1))
+    np.add.at(tab, (i1, i2), 1)
+
+    def ch2(x):
+        return x * (x - 1) / 2.0
+    correc = ch2(tab.sum(1)).sum() * ch2(tab.sum(0)).sum() / ch2(float(c1.size))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (ch2(tab).sum() - correc) / (0.5 * ch2(tab.sum(1)).sum() + 0.5 * ch2(tab.sum(0)).sum() - correc)
+
+
+def r_order(values):
+    """R's order(): ascending, stable, NA/NaN last."""
+    v = np.asarray(values, dtype=float)
+    idx = np.arange(v.size)
+    nan = np.isnan(v)
+    return np.concatenate([idx[~nan][np.argsort(v[~nan], kind="stable")], idx[nan]])
+
+
+def find_defining_features(X, ncat, K, lambda_, U, subsample, n_features=np.inf, measure="JS",
+                           step_size=np.inf, exponential_decay=True):
+    """Literal restatement of find_defining_features (/root/reference/R/predict.R:266-339) on the
+    numeric code matrix X (NaN = NA): every candidate is a full predict_class call with the dropped
+    columns all-NA (R/predict.R:66-67: a missing column is a column of NAs).  Features are column
+    indices; `subsample` replaces R's sample().  Returns (features, quality, rounds) where rounds
+    is the list of per-round divergence vectors (for the tests)."""
+    X = np.asarray(X, dtype=np.float64)
+    J = X.shape[1]
+    exponential_step = 2.0 if exponential_decay is True else (
+        float(exponential_decay) if not isinstance(exponential_decay, bool) else np.nan)
+    early_stop = 0 if np.isinf(n_features) else int(n_features)
+    Xs = X[np.asarray(subsample)]
+
+    def pred(cols):
+        Z = np.full_like(Xs, np.nan)
+        Z[:, cols] = Xs[:, cols]
+        return predict(Z, ncat, K, lambda_, U)[0]
+
+    def quality_of(q, p):
+        if measure == "JS":  # R/predict.R:304
+            with np.errstate(invalid="ignore", divide="ignore"):
+                return float(np.sum(q * (np.log(q) - np.log(p)) + p * (np.log(p) - np.log(q))) / 2)
+        return float(adjusted_rand(np.argmax(q, axis=1), np.argmax(p, axis=1)))
+
+    p = pred(list(range(J)))
+    remaining = list(range(J))
+    removed, quality, rounds = [], [], []
+    diverg = np.zeros(0)
+    while len(remaining) > early_stop:
+        diverg = np.zeros(len(remaining))
+        for n, i in enumerate(remaining):  # R/predict.R:299-310
+            v = quality_of(pred([c for c in remaining if c != i]), p)
+            diverg[n] = v if measure == "JS" else 1 - v
+        rounds.append((list(remaining), diverg.copy()))
+        exp_step = np.floor(len(remaining) * (1 - 1 / exponential_step)) if exponential_decay else np.inf
+        last_rm_idx = int(max(min(step_size, exp_step, len(remaining) - early_stop), 1))
+        order = r_order(diverg)[:last_rm_idx]
+        removed += [remaining[i] for i in order]
+        quality += [float(diverg[i]) for i in order]
+        remaining = [j for j in range(J) if j not in removed]
+    if measure == "ARI":
+        quality = [1 - q for q in quality]
+    if not np.isinf(n_features) and n_features != 0:
+        q = quality_of(pred(remaining), p)
+        head = -np.asarray(diverg[:len(remaining)], dtype=float)
+        return [remaining[i] for i in r_order(head)], q, rounds
+    return (removed + remaining)[::-1], quality[::-1], rounds
