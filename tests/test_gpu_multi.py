@@ -45,3 +45,26 @@ def test_single_process_two_devices_match_one(dp):
     assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < 1e-6
     assert np.array_equal(r["pred_class"], ref["pred_class"])
     assert np.max(np.abs(cp - r["class_prob"])) < 1e-12 and np.array_equal(pc, r["pred_class"])
+
+
+@pytest.mark.parametrize("measure", ["JS", "ARI"])
+def test_feature_divergence_two_devices_match_one(measure):
+    """mixdir_b200_feature_divergence on row shards (per-shard sums / contingency tables, one grouped
+    all-reduce) == the one-GPU pass, with and without a row subsample."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    pat = np.array([4, 2, 6, 3, 5, 2, 3, 8], dtype=np.int32)
+    N, K = 20_001, 5
+    codes, _ = synth.make_codes(9, N, pat, K, p_na=0.1)
+    with Engine(codes, pat) as eng:
+        r = eng.fit(K, synth.zeta_init(9, N, K).sum(axis=0), synth.phi_init(9, pat, K), max_iter=6,
+                    epsilon=-np.inf, want_class_prob=False, want_pred_class=False)
+    active = np.array([1, 1, 0, 1, 1, 1, 0, 1], dtype=np.uint8)
+    sub = np.random.default_rng(3).permutation(N)[:7000]
+    outs = []
+    for devs in (None, [0, 1]):
+        with Engine(codes, pat, devices=devs) as eng:
+            outs.append((eng.feature_divergence(K, r["lambda_"], r["category_prob"], active, measure),
+                         eng.feature_divergence(K, r["lambda_"], r["category_prob"], active, measure, rows=sub)))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-12, equal_nan=True)
