@@ -348,3 +348,34 @@ def test_feature_pair_units_against_oracle(K, J, p_na):
     assert pairs[(2, False)] == 0 and pairs[(4, False)] == 0
     if (J + 3) // 4 > (J - J // 2 + 3) // 4:  # pairing is used when it saves code words per row
         assert pairs[(2, True)] > 0 and pairs[(4, True)] > 0, pairs
+
+
+@pytest.mark.parametrize("engine", [2, 3, 4])
+def test_chunked_first_iteration_equals_resident_fit(engine):
+    """With n_cat_bound given, fit() starts while the upload is still in flight: the first pass runs
+    chunk by chunk (scan -> pack unit codes -> E+M on the rows that have landed, partial statistics
+    accumulate over the launches).  Same results as the fit on resident data, and as the oracle on a
+    prefix."""
+    pat = np.array([16, 12, 8, 4, 2, 10] * 6, dtype=np.int32)
+    N, K = 150_000, 24  # 8 upload chunks of 20480 rows; tiles straddle chunk ends for some plans
+    codes, _ = synth.make_codes(31, N, pat, K, p_na=0.03)
+    cs0 = synth.zeta_init(31, 4000, K).sum(axis=0) * (N / 4000.0)
+    p0 = synth.phi_init(31, pat, K)
+    ncb = int(codes.max())
+    with Engine(codes, pat) as eng:
+        eng.set_engine(engine)
+        a = eng.fit(K, cs0, p0, max_iter=3, epsilon=-np.inf, n_cat_bound=ncb)  # upload in flight
+        ta = eng.timing()
+        b = eng.fit(K, cs0, p0, max_iter=3, epsilon=-np.inf)                   # resident
+    assert ta["engine"] == engine
+    assert rel(a["convergence"], b["convergence"]) < 1e-12
+    assert np.array_equal(a["pred_class"], b["pred_class"])
+    np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-11, atol=1e-11)
+    sub = slice(0, 2500)
+    z0 = synth.zeta_init(31, 2500, K)
+    ref = po.fit(po.codes_to_r_matrix(codes[sub]), pat, K, 0, 1.0, 1.0, 0.1, 3, -np.inf, z0, p0)
+    with Engine(codes[sub], pat) as eng:
+        eng.set_engine(engine)
+        r = eng.fit(K, z0.sum(axis=0), p0, max_iter=3, epsilon=-np.inf, n_cat_bound=ncb)
+    assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
+    assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
