@@ -66,6 +66,23 @@ def ncu_traffic():
         return None
 
 
+def shared_memory_roofline(traffic, tm, N, J, K, kernel_ms, clocks):
+    """Secondary roofline: shared-memory wavefronts of the hot kernel -- counted by ncu
+    on the committed capture, scaled to this launch's rows -- over the kernel's duration, against the
+    pipe's peak of one wavefront per SM and cycle at the SM clock sampled during the run."""
+    if not (traffic and tm["engine"] == traffic.get("engine") and J == 60 and K == 32
+            and traffic.get("smem_wavefronts_per_row")):
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = 148
+    wf = traffic["smem_wavefronts_per_row"] * N
+    peak = sms * mhz * 1e6
+    ach = wf / (kernel_ms * 1e-3)
+    return {"bound": "shared-memory wavefronts", "achieved": ach, "peak": peak, "unit": "wavefronts/s",
+            "frac": ach / peak, "wavefronts_per_row": traffic["smem_wavefronts_per_row"],
+            "source": traffic.get("source")}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
 
@@ -347,6 +364,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,
                      "kernel_share_of_step": em_ms / loop_ms,
+                     "shared_memory": shared_memory_roofline(traffic, tm, N, J, K, em_ms_launch, clocks),
                      "note": "shared-memory bound, not HBM bound: see DESIGN.md 4.1 (per code, K fp64 "
                              "table gathers + K fp64 histogram read-modify-writes; the shared-memory "
                              "pipe runs at 80 % of its wavefront peak, profiles/README.md)"},
