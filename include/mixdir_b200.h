@@ -236,6 +236,15 @@ int mixdir_b200_set_pairing(mixdir_b200_handle* h, int on);
  * feature-table row collects.  Output arrays may be NULL. */
 int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, int* n_elements,
                           int* n_table_rows, int* desc, int* gbase, int* t2src, int* marg);
+/* Diagnostic, host only: the unit kernel's shared-memory placement of that plan for
+ * classes_per_cta (KC) classes per CTA.  Q = max(1, 16/KC) table rows of different elements share a
+ * 128-byte shared-memory row; element e sits at position e mod Q.  slot: n_table_rows entries, shared-
+ * memory slot (row * Q + position) of every unit-table row (row 0 of each position is the zero /
+ * scratch row of the padding elements); eoff_rot: 4 x n_elements byte offsets of element
+ * (e & ~3) | ((e + r) & 3) for rotation r.  desc / gbase are in the (re-ordered) element order. */
+int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs, int classes_per_cta,
+                            int* n_elements, int* n_table_rows, int* smem_rows, int* desc, int* gbase,
+                            int* slot, int* eoff_rot);
 
 const char* mixdir_b200_last_error(void);
 int mixdir_b200_abi_version(void);

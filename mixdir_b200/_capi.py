@@ -23,7 +23,7 @@ SYMBOLS = [
     "mixdir_b200_n_rows", "mixdir_b200_max_code", "mixdir_b200_n_missing", "mixdir_b200_fit",
     "mixdir_b200_predict", "mixdir_b200_feature_divergence", "mixdir_b200_estep",
     "mixdir_b200_last_timing",
-    "mixdir_b200_set_engine", "mixdir_b200_set_pairing", "mixdir_b200_unit_plan",
+    "mixdir_b200_set_engine", "mixdir_b200_set_pairing", "mixdir_b200_unit_plan", "mixdir_b200_unit_layout",
     "mixdir_b200_last_error",
     "mixdir_b200_abi_version",
 ]
@@ -79,6 +79,7 @@ def lib():
     L.mixdir_b200_set_engine.argtypes = [vp, C.c_int]
     L.mixdir_b200_set_pairing.argtypes = [vp, C.c_int]
     L.mixdir_b200_unit_plan.argtypes = [C.c_int, ip, C.c_int, ip, ip, vp, vp, vp, vp]
+    L.mixdir_b200_unit_layout.argtypes = [C.c_int, ip, C.c_int, C.c_int, ip, ip, ip, vp, vp, vp, vp]
     L.mixdir_b200_last_error.restype = C.c_char_p
     L.mixdir_b200_abi_version.restype = C.c_int
     _lib = L

@@ -825,6 +825,7 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 typedef void (*fused_fn)(FusedArgs);
 typedef void (*bucket_fn)(BucketArgs);
 typedef void (*units_fn)(UnitArgs);
+static void layout_units(UnitPlan* up, int KC);
 
 static fused_fn pick_fused(int KC, int CB, int RG) {
 #define PICK(kc, cb, rg) \
@@ -1115,6 +1116,29 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
   if (best.engine != 4) return false;
   *out = best;
   return true;
+}
+
+// host-only view of the unit kernel's shared-memory placement for KC classes per CTA (CPU tests)
+extern "C" int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs,
+                                       int classes_per_cta, int* n_elements, int* n_table_rows,
+                                       int* smem_rows, int* desc, int* gbase, int* slot,
+                                       int* eoff_rot) {
+  if (classes_per_cta != 4 && classes_per_cta != 8 && classes_per_cta != 16 && classes_per_cta != 32)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "classes_per_cta must be 4, 8, 16 or 32");
+  mixdir_b200_handle h;
+  RET_IF(init_geometry(&h, 1, n_features, ncat));
+  UnitPlan up;
+  if (n_pairs < 0 || !make_units(&h, n_pairs, &up, true))
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "this many pairs cannot be formed (a pair code must fit a byte)");
+  layout_units(&up, classes_per_cta);
+  if (n_elements) *n_elements = up.U;
+  if (n_table_rows) *n_table_rows = up.NR2;
+  if (smem_rows) *smem_rows = up.srows;
+  if (desc) memcpy(desc, up.desc.data(), up.desc.size() * sizeof(UnitDesc));
+  if (gbase) memcpy(gbase, up.gbase.data(), up.gbase.size() * sizeof(int));
+  if (slot) memcpy(slot, up.slot.data(), up.slot.size() * sizeof(int));
+  if (eoff_rot) memcpy(eoff_rot, up.eoff_rot.data(), up.eoff_rot.size() * sizeof(int));
+  return MIXDIR_B200_OK;
 }
 
 // engine 2: k_em_fused (row-owned M-step, read-modify-write per row and unit)

@@ -97,3 +97,72 @@ def test_unit_plan_rejects_pairs_that_do_not_fit_a_byte():
     assert unit_plan([3, 3, 3], 2) is None     # more pairs than features allow
     ident = unit_plan([3, 4, 5], 0)
     assert ident["NR2"] == 15 and ident["U"] == 4  # identity: padded features, feature tables
+
+
+def unit_layout(ncat, m, KC):
+    L = _capi.lib()
+    ncat = np.ascontiguousarray(ncat, dtype=np.int32)
+    J = ncat.size
+    ip = C.POINTER(C.c_int)
+    U, NR2, SR = C.c_int(), C.c_int(), C.c_int()
+    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, KC, C.byref(U), C.byref(NR2),
+                                     C.byref(SR), None, None, None, None) == 0
+    desc = np.zeros((U.value, 4), dtype=np.int32)
+    gbase = np.zeros(U.value, dtype=np.int32)
+    slot = np.zeros(NR2.value, dtype=np.int32)
+    eoff = np.zeros((4, U.value), dtype=np.int32)
+    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, KC, C.byref(U), C.byref(NR2),
+                                     C.byref(SR), desc.ctypes.data, gbase.ctypes.data,
+                                     slot.ctypes.data, eoff.ctypes.data) == 0
+    return dict(U=U.value, NR2=NR2.value, srows=SR.value, desc=desc, gbase=gbase, slot=slot, eoff=eoff)
+
+
+@pytest.mark.parametrize("KC", [8, 16, 32, 4])
+@pytest.mark.parametrize("ncat,m", [([16, 12, 8, 4, 2, 10] * 4, 10), ([16, 12, 8, 4, 2, 10] * 4, 0),
+                                    ([2, 3, 4, 5, 6], 2), ([7], 0)])
+def test_unit_layout_bank_positions_and_gather(ncat, m, KC):
+    """The shared-memory placement of k_em_units (engine.cu: layout_units), emulated in numpy: every
+    unit-table row has its own slot, element e sits at bank position e mod Q, the slots of one warp
+    instruction cover the positions evenly under the slot rotation, and gathering through
+    (eoff_rot, code) from the emulated shared-memory table returns T2[gbase + code]."""
+    ncat = np.asarray(ncat)
+    lay = unit_layout(ncat, m, KC)
+    up = unit_plan(ncat, m) if m > 0 else None
+    Q = 1 if KC >= 16 else 16 // KC
+    RS = max(128, KC * 8)
+    U, NR2, srows = lay["U"], lay["NR2"], lay["srows"]
+    assert U % 4 == 0 and (up is None or NR2 == up["NR2"])
+    nrows = np.zeros(U, dtype=int)  # rows per element, from its descriptor
+    for e, (oa, ob, mul, _) in enumerate(lay["desc"]):
+        if oa >= 0:
+            nrows[e] = (ncat[oa] + 1) * (mul if ob >= 0 else 1)
+    assert nrows.sum() == NR2
+    slot = lay["slot"]
+    assert len(set(slot.tolist())) == NR2 and slot.min() >= Q and slot.max() < srows * Q  # row 0 is reserved
+    for e in range(U):
+        if nrows[e]:
+            sl = slot[lay["gbase"][e]:lay["gbase"][e] + nrows[e]]
+            assert np.all(sl % Q == e % Q) and np.all(np.diff(sl) == Q)  # one position, consecutive rows
+            assert lay["eoff"][0, e] == sl[0] * KC * 8
+        else:
+            assert lay["eoff"][0, e] == (e % Q) * KC * 8  # padding -> zero row of its position
+    for r in range(4):
+        for e in range(U):
+            assert lay["eoff"][r, e] == lay["eoff"][0, (e & ~3) | ((e + r) & 3)]
+    # balanced stacks: the tallest position stack is the table height
+    heights = [1 + sum(nrows[e] for e in range(U) if e % Q == q) for q in range(Q)]
+    assert srows == max(heights)
+    # slots s = 0 .. 32/KC - 1 of one instruction at sub-step f: positions covered evenly
+    RPW = 32 // KC
+    for f in range(4):
+        pos = [((0 & ~3) | ((f + (s & 3)) & 3)) % Q for s in range(RPW)]
+        assert all(pos.count(q) == RPW // Q for q in range(Q))
+    # emulated gather for class kc = 0: shared-memory table as doubles, slot * KC + kc
+    rng = np.random.default_rng(1)
+    T2 = rng.normal(size=NR2)
+    Ts = np.zeros(srows * (RS // 8))
+    Ts[slot * KC] = T2
+    for e in range(U):
+        for code in range(nrows[e]):
+            addr = lay["eoff"][0, e] + code * RS  # bytes
+            assert Ts[addr // 8] == T2[lay["gbase"][e] + code]
