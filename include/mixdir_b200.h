@@ -230,21 +230,25 @@ int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine);
  * re-association inside the per-row logit sum (mixdir_impl.cpp:77-82).  0 switches it off. */
 int mixdir_b200_set_pairing(mixdir_b200_handle* h, int on);
 /* Diagnostic, host only (no device): the unit plan with n_pairs feature pairs for 1-byte codes.
- * desc: n_elements x {byte offset of feature a (<0: padding), of feature b (<0: single), C_b+1, 0};
+ * has_na (nullable; the unit kernel passes the upload scan's result): has_na[j] == 0 = feature j holds
+ * no NA anywhere and gets no NA row (its unit-local code is x - 1); NULL = every feature keeps its NA row.
+ * desc: n_elements x {byte offset of feature a (<0: padding), of feature b (<0: single), unit-local
+ * codes of b, bit 0/1 = a/b without NA row};
  * gbase: first unit-table row of each element; t2src: n_table_rows x {feature-table row a, row b or
  * -1} (only written when n_pairs > 0); marg: sum_j(C_j+1) x {start, stride, count, 0}: the unit rows a
  * feature-table row collects.  Output arrays may be NULL. */
-int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, int* n_elements,
-                          int* n_table_rows, int* desc, int* gbase, int* t2src, int* marg);
+int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, const unsigned char* has_na,
+                          int* n_elements, int* n_table_rows, int* desc, int* gbase, int* t2src,
+                          int* marg);
 /* Diagnostic, host only: the unit kernel's shared-memory placement of that plan for
  * classes_per_cta (KC) classes per CTA.  Q = max(1, 16/KC) table rows of different elements share a
  * 128-byte shared-memory row; element e sits at position e mod Q.  slot: n_table_rows entries, shared-
  * memory slot (row * Q + position) of every unit-table row (row 0 of each position is the zero /
  * scratch row of the padding elements); eoff_rot: 4 x n_elements byte offsets of element
  * (e & ~3) | ((e + r) & 3) for rotation r.  desc / gbase are in the (re-ordered) element order. */
-int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs, int classes_per_cta,
-                            int* n_elements, int* n_table_rows, int* smem_rows, int* desc, int* gbase,
-                            int* slot, int* eoff_rot);
+int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs, const unsigned char* has_na,
+                            int classes_per_cta, int* n_elements, int* n_table_rows, int* smem_rows,
+                            int* desc, int* gbase, int* slot, int* eoff_rot);
 
 const char* mixdir_b200_last_error(void);
 int mixdir_b200_abi_version(void);

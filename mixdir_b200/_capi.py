@@ -78,8 +78,8 @@ def lib():
     L.mixdir_b200_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.mixdir_b200_set_engine.argtypes = [vp, C.c_int]
     L.mixdir_b200_set_pairing.argtypes = [vp, C.c_int]
-    L.mixdir_b200_unit_plan.argtypes = [C.c_int, ip, C.c_int, ip, ip, vp, vp, vp, vp]
-    L.mixdir_b200_unit_layout.argtypes = [C.c_int, ip, C.c_int, C.c_int, ip, ip, ip, vp, vp, vp, vp]
+    L.mixdir_b200_unit_plan.argtypes = [C.c_int, ip, C.c_int, vp, ip, ip, vp, vp, vp, vp]
+    L.mixdir_b200_unit_layout.argtypes = [C.c_int, ip, C.c_int, vp, C.c_int, ip, ip, ip, vp, vp, vp, vp]
     L.mixdir_b200_last_error.restype = C.c_char_p
     L.mixdir_b200_abi_version.restype = C.c_int
     _lib = L

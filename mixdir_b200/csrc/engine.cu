@@ -193,6 +193,7 @@ struct Shard {
   std::vector<int64_t> up_end;  // exclusive row end of chunk c
   size_t up_seen = 0;           // chunks already waited for + scanned on the compute stream
   ScanOut* d_scan = nullptr;    // NA count / largest code / validity, accumulated over chunks
+  unsigned int* d_na_feat = nullptr;  // [J] NA cells per feature (null: J too large to count)
   double* d_stage[2] = {nullptr, nullptr};  // fp64 staging of create_from_r_matrix
   // page-locked, device-mapped scratch for the small per-fit inputs: kernels pull them over
   // PCIe themselves, so they do not queue behind the bulk upload on the H2D copy engine
@@ -208,6 +209,7 @@ struct mixdir_b200_handle {
   int64_t sum_ncat = 0;
   std::vector<int> ncat, rowoff, rowoff_pad;
   std::vector<int64_t> ragoff1;  // ragged offsets for K = 1 (scaled by K at use)
+  std::vector<uint8_t> has_na;   // [J] 0: the feature holds no NA anywhere (valid once scan_resolved)
   std::vector<Shard> shards;
   int rank = 0, world = 1;   // multi-process flavour
   int engine_pref = 0;
@@ -378,6 +380,7 @@ static void free_shard(Shard& s) {
   free_workspace(s);
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
   dfree(s.d_ragoff); dfree(s.d_na_row); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
+  dfree(s.d_na_feat);
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
   dfree(s.d_slot); dfree(s.d_eoff);
   s.unit_valid = false;
@@ -437,6 +440,8 @@ static int init_geometry(mixdir_b200_handle* h, int code_bytes, int J, const int
   return MIXDIR_B200_OK;
 }
 
+constexpr int kMaxNaFeat = 8192;  // per-feature NA counters of the scan live in shared memory
+
 static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   CU_TRY(cudaSetDevice(s.device));
   int cc_major = 0;  // (cudaGetDeviceProperties costs milliseconds; these attribute reads do not)
@@ -449,6 +454,10 @@ static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   CU_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
   RET_IF(dalloc(&s.d_scan, 1));
   CU_TRY(cudaMemsetAsync(s.d_scan, 0, sizeof(ScanOut), s.stream));
+  if (h->J <= kMaxNaFeat) {
+    RET_IF(dalloc(&s.d_na_feat, (size_t)h->J));
+    CU_TRY(cudaMemsetAsync(s.d_na_feat, 0, (size_t)h->J * sizeof(unsigned int), s.stream));
+  }
   CU_TRY(cudaEventCreate(&s.ev_loop0));
   CU_TRY(cudaEventCreate(&s.ev_loop1));
   CU_TRY(cache::pin_get((void**)&s.h_status, sizeof(IterStatus)));
@@ -551,10 +560,11 @@ static int consume_upload(mixdir_b200_handle* h, Shard& s, size_t upto) {
     const int64_t nr = s.up_end[c] - r0;
     const uint8_t* base = s.d_codes + (size_t)r0 * h->row_bytes;
     const int grid = (int)std::min<int64_t>(s.sm_count * 8, (nr * h->WPR + 255) / 256);
+    const size_t sm = s.d_na_feat ? (size_t)h->J * sizeof(unsigned int) : 0;
     if (h->CB == 1)
-      k_scan_codes<1><<<grid, 256, 0, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan);
+      k_scan_codes<1><<<grid, 256, sm, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan, s.d_na_feat);
     else
-      k_scan_codes<2><<<grid, 256, 0, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan);
+      k_scan_codes<2><<<grid, 256, sm, s.stream>>>(base, h->row_bytes, nr, h->J, s.d_ncat, s.d_scan, s.d_na_feat);
     CU_TRY(cudaGetLastError());
   }
   return MIXDIR_B200_OK;
@@ -569,11 +579,17 @@ static int resolve_scan(mixdir_b200_handle* h) {
   for (auto& s : h->shards) {
     if (!s.up_ev.empty()) RET_IF(consume_upload(h, s, s.up_ev.size() - 1));
   }
+  std::vector<long long> na_any(h->J, 0);  // > 0: the feature holds an NA on some shard / rank
+  std::vector<unsigned int> na_cnt(h->J);
   for (auto& s : h->shards) {
     CU_TRY(cudaSetDevice(s.device));
     ScanOut o;
     CU_TRY(cudaMemcpyAsync(&o, s.d_scan, sizeof o, cudaMemcpyDeviceToHost, s.stream));
+    if (s.d_na_feat)
+      CU_TRY(cudaMemcpyAsync(na_cnt.data(), s.d_na_feat, (size_t)h->J * sizeof(unsigned int),
+                             cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
+    for (int j = 0; j < h->J; j++) na_any[j] += s.d_na_feat ? (long long)(na_cnt[j] != 0) : 1;
     dfree(s.d_stage[0]);
     dfree(s.d_stage[1]);
     miss += (int64_t)o.n_missing;
@@ -595,7 +611,16 @@ static int resolve_scan(mixdir_b200_handle* h) {
     miss = v[0];
     mx = (int)v[1];
     bad = (int)v[2];
+    long long* dn = nullptr;
+    RET_IF(dalloc(&dn, (size_t)h->J));
+    CU_TRY(cudaMemcpyAsync(dn, na_any.data(), (size_t)h->J * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+    NCCL_TRY(nccl::AllReduce(dn, dn, (size_t)h->J, nccl::kInt64, nccl::kMax, s.comm, s.stream));
+    CU_TRY(cudaMemcpyAsync(na_any.data(), dn, (size_t)h->J * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    dfree(dn);
   }
+  h->has_na.assign(h->J, 1);
+  for (int j = 0; j < h->J; j++) h->has_na[j] = na_any[j] != 0;
   h->n_missing = miss;
   h->max_code = mx;
   h->scan_resolved = true;
@@ -911,7 +936,10 @@ static void identity_units(const mixdir_b200_handle* h, UnitPlan* up) {
 // categories are paired smallest-with-largest, which minimises the added table rows
 // sum (C_a+1)(C_b+1) for that many pairs; every pair code must still fit a byte.
 // Returns false if some pair would need more than 256 codes.
-static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool always_packed = false) {
+// has_na (nullable, engine 4 only): features with has_na[j] == 0 hold no NA anywhere (upload
+// scan) and get no NA row -- their unit-local code is x - 1 -- which shrinks the pair tables.
+static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool always_packed = false,
+                       const uint8_t* has_na = nullptr) {
   const int J = h->J;
   if (m <= 0 && !always_packed) {
     identity_units(h, up);
@@ -919,13 +947,18 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool al
   }
   if (m < 0) m = 0;
   if (h->CB != 1 || 2 * m > J) return false;
+  std::vector<int> lev(J), sub(J);  // unit-local codes per feature, and what is subtracted from x
+  for (int j = 0; j < J; j++) {
+    sub[j] = (has_na && !has_na[j]) ? 1 : 0;
+    lev[j] = h->ncat[j] + 1 - sub[j];
+  }
   std::vector<int> order(J);
   for (int j = 0; j < J; j++) order[j] = j;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->ncat[a] < h->ncat[b]; });
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lev[a] < lev[b]; });
   std::vector<int> partner(J, -1);
   for (int i = 0; i < m; i++) {
     const int a = order[i], b = order[2 * m - 1 - i];
-    if ((h->ncat[a] + 1) * (h->ncat[b] + 1) > 256) return false;
+    if (lev[a] * lev[b] > 256) return false;
     partner[a] = b;
     partner[b] = a;
   }
@@ -937,25 +970,25 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool al
   for (int j = 0; j < J; j++) {
     const int b = partner[j];
     if (b >= 0 && b < j) continue;  // emitted with its lower-index partner
-    const int Ca = h->ncat[j];
+    const int Ca = h->ncat[j], La = lev[j], sa = sub[j];
     if (b < 0) {
-      up->desc.push_back(UnitDesc{j, -1, 1, 0});
+      up->desc.push_back(UnitDesc{j, -1, 1, sa});
       up->gbase.push_back(nr2);
-      up->erows.push_back(Ca + 1);
-      for (int c = 0; c <= Ca; c++) up->t2src.push_back(make_int2(h->rowoff[j] + c, -1));
-      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c, 0, 1, 0};
-      nr2 += Ca + 1;
+      up->erows.push_back(La);
+      for (int u = 0; u < La; u++) up->t2src.push_back(make_int2(h->rowoff[j] + u + sa, -1));
+      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c - sa, 0, 1, 0};
+      nr2 += La;
     } else {
-      const int Cb = h->ncat[b], mul = Cb + 1;
-      up->desc.push_back(UnitDesc{j, b, mul, 0});
+      const int Cb = h->ncat[b], Lb = lev[b], sb = sub[b];
+      up->desc.push_back(UnitDesc{j, b, Lb, sa | (sb << 1)});
       up->gbase.push_back(nr2);
-      up->erows.push_back((Ca + 1) * mul);
-      for (int ca = 0; ca <= Ca; ca++)
-        for (int cb = 0; cb <= Cb; cb++)
-          up->t2src.push_back(make_int2(h->rowoff[j] + ca, h->rowoff[b] + cb));
-      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + c * mul, 1, mul, 0};
-      for (int c = 1; c <= Cb; c++) up->marg[h->rowoff[b] + c] = MargDesc{nr2 + c, mul, Ca + 1, 0};
-      nr2 += (Ca + 1) * mul;
+      up->erows.push_back(La * Lb);
+      for (int ua = 0; ua < La; ua++)
+        for (int ub = 0; ub < Lb; ub++)
+          up->t2src.push_back(make_int2(h->rowoff[j] + ua + sa, h->rowoff[b] + ub + sb));
+      for (int c = 1; c <= Ca; c++) up->marg[h->rowoff[j] + c] = MargDesc{nr2 + (c - sa) * Lb, 1, Lb, 0};
+      for (int c = 1; c <= Cb; c++) up->marg[h->rowoff[b] + c] = MargDesc{nr2 + (c - sb), Lb, La, 0};
+      nr2 += La * Lb;
     }
   }
   up->NR2 = nr2;
@@ -971,12 +1004,13 @@ static bool make_units(const mixdir_b200_handle* h, int m, UnitPlan* up, bool al
 
 // host-only view of a unit plan (no device needed): lets the CPU tests check the invariants
 // the device code relies on.  Arrays may be NULL (sizes only).
-extern "C" int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs, int* n_elements,
+extern "C" int mixdir_b200_unit_plan(int n_features, const int* ncat, int n_pairs,
+                                     const unsigned char* has_na, int* n_elements,
                                      int* n_table_rows, int* desc, int* gbase, int* t2src, int* marg) {
   mixdir_b200_handle h;
   RET_IF(init_geometry(&h, 1, n_features, ncat));
   UnitPlan up;
-  if (n_pairs < 0 || !make_units(&h, n_pairs, &up))
+  if (n_pairs < 0 || !make_units(&h, n_pairs, &up, has_na != nullptr, has_na))
     return fail(MIXDIR_B200_BAD_ARGUMENT, "this many pairs cannot be formed (a pair code must fit a byte)");
   if (n_elements) *n_elements = up.U;
   if (n_table_rows) *n_table_rows = up.NR2;
@@ -1053,6 +1087,10 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
   int fKC = -1, fRG = -1, fM = -1, fFPG = -1, fW = -1;
   if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN"))
     sscanf(f, "%d,%d,%d,%d,%d", &fKC, &fRG, &fM, &fFPG, &fW);
+  // NA rows only for features that hold NAs -- known once the upload scan has been read back
+  // (not while the first, chunked iteration overlaps the upload)
+  const uint8_t* na = (h->scan_resolved && (int)h->has_na.size() == h->J && !getenv("MIXDIR_B200_KEEP_NA_ROWS"))
+                          ? h->has_na.data() : nullptr;
   Plan best;
   double best_cost = 1e300;
   const int kcs[3] = {32, 16, 8};
@@ -1084,7 +1122,7 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       const int w_lo = (h->J - m_hi + 3) / 4, w_hi = (h->J + 3) / 4;
       for (int w = w_lo; w <= w_hi; w++) {
         const int m = fM >= 0 ? m_hi : std::max(0, h->J - 4 * w);
-        if (m > m_hi || !make_units(h, m, &up, true)) continue;
+        if (m > m_hi || !make_units(h, m, &up, true, na)) continue;
         const size_t tot = shape(up);
         if (tot > (size_t)s.smem_optin) continue;
         c.smem = tot;
@@ -1098,15 +1136,19 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       if (!pick_units(KC, RG, c.FPG)) continue;
       c.n_clusters = plan_occupancy(h, s, c);
       if (c.n_clusters < 1) continue;
-      // cost model (shared-memory wavefronts per row over all CTAs of a cluster, per SM in use):
-      // 6 wavefronts per element and 256 bytes of classes, a per-row term every CTA repeats
-      // (code words, soft-max, exchange), and per-tile barriers spread over the tile's rows
+      // Cost model, in shared-memory cycles per row summed over the CTAs of a cluster and divided
+      // by the fraction of SMs the cluster shape can occupy.  Per CTA and row: 6 wavefronts per
+      // element and 256 bytes of classes, plus the work every CTA repeats per row whatever its class
+      // slice (code words, soft-max, exchange, barriers; fitted to the plan sweeps in
+      // profiles/README.md: ~65 cycles at KC=16, ~52 at KC=8); fewer row groups per lane hide less
+      // latency; per-tile barriers are spread over the tile's rows.
       const double used = std::min(1.0, (double)c.n_clusters * P / s.sm_count);
       const int G = up.U / c.FPG;
-      const double per_row = P * (up.U * 6.0 + 60.0) / RPW;
+      const double ovh = KC == 8 ? 52.0 : (KC == 16 ? 65.0 : 80.0);
+      const double rgpen = RG == 8 ? 1.0 : (RG == 4 ? 1.05 : 1.12);
+      const double per_row = P * (up.U * 6.0 / RPW + ovh) * rgpen / used;
       const double per_tile = P * (G * 60.0 + 1500.0) / c.R;
-      const double starve = c.W >= 12 ? 1.0 : 1.0 + 0.03 * (12 - c.W);  // few warps hide less latency
-      const double cost = (per_row + per_tile) * starve / used;
+      const double cost = per_row + per_tile;
       if (cost < best_cost) {
         best_cost = cost;
         best = c;
@@ -1120,7 +1162,8 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
 
 // host-only view of the unit kernel's shared-memory placement for KC classes per CTA (CPU tests)
 extern "C" int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs,
-                                       int classes_per_cta, int* n_elements, int* n_table_rows,
+                                       const unsigned char* has_na, int classes_per_cta,
+                                       int* n_elements, int* n_table_rows,
                                        int* smem_rows, int* desc, int* gbase, int* slot,
                                        int* eoff_rot) {
   if (classes_per_cta != 4 && classes_per_cta != 8 && classes_per_cta != 16 && classes_per_cta != 32)
@@ -1128,7 +1171,7 @@ extern "C" int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pa
   mixdir_b200_handle h;
   RET_IF(init_geometry(&h, 1, n_features, ncat));
   UnitPlan up;
-  if (n_pairs < 0 || !make_units(&h, n_pairs, &up, true))
+  if (n_pairs < 0 || !make_units(&h, n_pairs, &up, true, has_na))
     return fail(MIXDIR_B200_BAD_ARGUMENT, "this many pairs cannot be formed (a pair code must fit a byte)");
   layout_units(&up, classes_per_cta);
   if (n_elements) *n_elements = up.U;

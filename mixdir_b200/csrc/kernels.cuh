@@ -77,9 +77,16 @@ struct ScanOut {
   int bad;  // some code exceeded its feature's C_j
 };
 
+// na_feat (nullable): per-feature NA counts, collected in shared memory (J * 4 bytes of dynamic
+// shared memory) -- a feature that never holds an NA needs no NA row in the unit tables.
 template <int CB>
 __global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, int64_t n_rows, int J,
-                             const int* __restrict__ ncat, ScanOut* out) {
+                             const int* __restrict__ ncat, ScanOut* out, unsigned int* na_feat) {
+  extern __shared__ unsigned int na_s[];
+  if (na_feat) {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) na_s[j] = 0u;
+    __syncthreads();
+  }
   unsigned long long miss = 0;
   int mx = 0, bad = 0;
   // one 32-bit code word per thread and step; (row, word-in-row) advance incrementally so the
@@ -101,6 +108,7 @@ __global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, i
       if (j < J) {
         const int x = CB == 1 ? (int)((cw >> (8 * f)) & 0xffu) : (int)((cw >> (16 * f)) & 0xffffu);
         miss += (x == 0);
+        if (x == 0 && na_feat) atomicAdd(&na_s[j], 1u);
         mx = max(mx, x);
         bad |= (x > __ldg(ncat + j));
       }
@@ -121,6 +129,11 @@ __global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, i
     atomicAdd(&out->n_missing, miss);
     atomicMax(&out->max_code, mx);
     if (bad) atomicOr(&out->bad, 1);
+  }
+  if (na_feat) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += blockDim.x)
+      if (na_s[j]) atomicAdd(&na_feat[j], na_s[j]);
   }
 }
 
@@ -574,8 +587,8 @@ __global__ void k_reduce_partials(ReduceArgs a) {
 struct UnitDesc {
   int off_a;  // byte offset of feature ja inside a raw code row; < 0: padding element (code 0)
   int off_b;  // byte offset of feature jb; < 0: single feature
-  int mul;    // C_b + 1 (1 for a single feature)
-  int pad;
+  int mul;    // number of unit-local codes of feature b: C_b + 1, or C_b if b never holds an NA
+  int pad;    // bit 0 / bit 1: feature a / b has no NA row (unit-local code = x - 1)
 };
 
 // raw row-major codes (1 byte per cell) -> unit codes, WPRu 32-bit words per row.
@@ -606,9 +619,9 @@ __global__ void k_pack_units(const uint8_t* __restrict__ raw, int row_bytes, int
       const int4 uu = __ldg(reinterpret_cast<const int4*>(units) + col * 4 + f);
       const UnitDesc u = {uu.x, uu.y, uu.z, uu.w};
       uint32_t c = 0;
-      if (u.off_a >= 0) {
-        c = r[u.off_a];
-        if (u.off_b >= 0) c = c * (uint32_t)u.mul + r[u.off_b];
+      if (u.off_a >= 0) {  // pad bit 0 / 1: feature a / b never holds an NA, its codes start at 0
+        c = r[u.off_a] - (uint32_t)(u.pad & 1);
+        if (u.off_b >= 0) c = c * (uint32_t)u.mul + (r[u.off_b] - (uint32_t)((u.pad >> 1) & 1));
       }
       cw |= (c & 0xffu) << (8 * f);
     }

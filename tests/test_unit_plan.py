@@ -10,13 +10,15 @@ import pytest
 from mixdir_b200 import _capi
 
 
-def unit_plan(ncat, m):
+def unit_plan(ncat, m, has_na=None):
     L = _capi.lib()
     ncat = np.ascontiguousarray(ncat, dtype=np.int32)
     J = ncat.size
     U, NR2 = C.c_int(), C.c_int()
     ip = C.POINTER(C.c_int)
-    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, C.byref(U), C.byref(NR2), None, None,
+    na = None if has_na is None else np.ascontiguousarray(has_na, dtype=np.uint8)
+    nap = None if na is None else na.ctypes.data
+    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, nap, C.byref(U), C.byref(NR2), None, None,
                                  None, None)
     if st != 0:
         return None
@@ -25,7 +27,7 @@ def unit_plan(ncat, m):
     gbase = np.zeros(U.value, dtype=np.int32)
     t2src = np.full((NR2.value, 2), -1, dtype=np.int32)
     marg = np.zeros((NR, 4), dtype=np.int32)
-    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, C.byref(U), C.byref(NR2),
+    st = L.mixdir_b200_unit_plan(J, ncat.ctypes.data_as(ip), m, nap, C.byref(U), C.byref(NR2),
                                  desc.ctypes.data, gbase.ctypes.data, t2src.ctypes.data, marg.ctypes.data)
     assert st == 0
     return dict(U=U.value, NR2=NR2.value, desc=desc, gbase=gbase, t2src=t2src, marg=marg)
@@ -33,27 +35,32 @@ def unit_plan(ncat, m):
 
 def pack(codes, desc):
     out = np.zeros((codes.shape[0], desc.shape[0]), dtype=np.int64)
-    for e, (oa, ob, mul, _) in enumerate(desc):
+    for e, (oa, ob, mul, flags) in enumerate(desc):
         if oa < 0:
             continue
-        out[:, e] = codes[:, oa]
+        out[:, e] = codes[:, oa] - (flags & 1)
         if ob >= 0:
-            out[:, e] = out[:, e] * mul + codes[:, ob]
+            out[:, e] = out[:, e] * mul + (codes[:, ob] - ((flags >> 1) & 1))
     return out
 
 
+@pytest.mark.parametrize("na_mode", ["all", "none", "some"])
 @pytest.mark.parametrize("ncat,m", [
     ([16, 12, 8, 4, 2, 10] * 3, 9), ([16, 12, 8, 4, 2, 10] * 3, 4), ([2, 3, 4, 5, 6], 2),
     ([10] * 7, 3), ([1, 1, 1], 1), ([15, 15, 3], 1), ([120, 1, 1, 100], 2)])
-def test_unit_plan_reproduces_gather_and_scatter(ncat, m):
+def test_unit_plan_reproduces_gather_and_scatter(ncat, m, na_mode):
     rng = np.random.default_rng(7)
     ncat = np.asarray(ncat)
     J, N, K = ncat.size, 400, 3
-    up = unit_plan(ncat, m)
+    # features without any NA lose their NA row (has_na[j] == 0); "all" = the default plan
+    has_na = {"all": None, "none": np.zeros(J, dtype=np.uint8),
+              "some": (np.arange(J) % 3 == 0).astype(np.uint8)}[na_mode]
+    up = unit_plan(ncat, m, has_na)
     assert up is not None
     rowoff = np.concatenate([[0], np.cumsum(ncat + 1)[:-1]])
     NR = int((ncat + 1).sum())
-    codes = np.stack([rng.integers(0, c + 1, size=N) for c in ncat], axis=1)  # 0 = NA
+    lo = np.zeros(J, dtype=int) if has_na is None else 1 - has_na.astype(int)
+    codes = np.stack([rng.integers(lo[j], c + 1, size=N) for j, c in enumerate(ncat)], axis=1)  # 0 = NA
     u = pack(codes, up["desc"])
     assert up["U"] % 4 == 0 and u.max() <= 255
     n_real = int((up["desc"][:, 0] >= 0).sum())
@@ -72,12 +79,14 @@ def test_unit_plan_reproduces_gather_and_scatter(ncat, m):
     lhs = T2[g2[:, real]].sum(axis=1)
     rhs = T[rowoff[None, :] + codes].sum(axis=1)
     np.testing.assert_allclose(lhs, rhs, rtol=0, atol=1e-12)
-    # padding elements point at a row whose T2 is zero
-    assert np.all(T2[g2[:, ~real]] == 0.0)
+    # padding elements point at a row whose T2 is zero (plans that keep every NA row: that is what
+    # k_em_fused relies on; the unit kernel gives padding its own zero row instead)
+    if has_na is None:
+        assert np.all(T2[g2[:, ~real]] == 0.0)
     # scatter: unit statistics marginalised by marg == feature statistics
     z = rng.random(size=(N, K))
     S2 = np.zeros((up["NR2"], K))
-    for e in range(up["U"]):
+    for e in np.flatnonzero(real):
         np.add.at(S2, g2[:, e], z)
     S = np.zeros((NR, K))
     for j in range(J):
@@ -97,6 +106,8 @@ def test_unit_plan_rejects_pairs_that_do_not_fit_a_byte():
     assert unit_plan([3, 3, 3], 2) is None     # more pairs than features allow
     ident = unit_plan([3, 4, 5], 0)
     assert ident["NR2"] == 15 and ident["U"] == 4  # identity: padded features, feature tables
+    lean = unit_plan([3, 4, 5], 1, np.zeros(3, dtype=np.uint8))
+    assert lean["NR2"] == 3 * 4 + 5  # (3 x 4) pair without NA rows + the single feature with 5
 
 
 def unit_layout(ncat, m, KC):
@@ -105,13 +116,13 @@ def unit_layout(ncat, m, KC):
     J = ncat.size
     ip = C.POINTER(C.c_int)
     U, NR2, SR = C.c_int(), C.c_int(), C.c_int()
-    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, KC, C.byref(U), C.byref(NR2),
+    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, None, KC, C.byref(U), C.byref(NR2),
                                      C.byref(SR), None, None, None, None) == 0
     desc = np.zeros((U.value, 4), dtype=np.int32)
     gbase = np.zeros(U.value, dtype=np.int32)
     slot = np.zeros(NR2.value, dtype=np.int32)
     eoff = np.zeros((4, U.value), dtype=np.int32)
-    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, KC, C.byref(U), C.byref(NR2),
+    assert L.mixdir_b200_unit_layout(J, ncat.ctypes.data_as(ip), m, None, KC, C.byref(U), C.byref(NR2),
                                      C.byref(SR), desc.ctypes.data, gbase.ctypes.data,
                                      slot.ctypes.data, eoff.ctypes.data) == 0
     return dict(U=U.value, NR2=NR2.value, srows=SR.value, desc=desc, gbase=gbase, slot=slot, eoff=eoff)
