@@ -61,3 +61,27 @@ List mixdir_vi_b200_cpp(NumericMatrix X,            // codes 1..C_j, NA  (R/mixd
                       _["class_prob"] = class_prob, _["U_flat"] = U, _["phi_flat"] = phi,
                       _["prior"] = prior);
 }
+
+// One round of find_defining_features() (R/predict.R:299-310): the quality loss for every
+// remaining variable if it were removed as well, in ONE device pass instead of one
+// predict.mixdir() call per variable.  X is the coded subsample X[subsample, ] (same coding as the
+// training data: the levels of mixdir_obj$category_prob), `active` marks the remaining variables.
+// Element ncol(X) + 1 of the result is the value for the active set itself (the final quality of
+// R/predict.R:326-331).  measure: FALSE = "JS", TRUE = "ARI" (returned as 1 - ARI like the R code).
+// [[Rcpp::export]]
+NumericVector feature_divergence_b200_cpp(NumericMatrix X, IntegerVector ncat, NumericVector lambda,
+                                          NumericVector category_prob_flat,  // unlist(category_prob)
+                                          LogicalVector active, bool ari) {
+  const int N = X.nrow(), J = X.ncol(), K = lambda.size();
+  mixdir_b200_handle* h = nullptr;
+  int st = mixdir_b200_create_from_r_matrix(X.begin(), N, J, ncat.begin(), 0, nullptr, &h);
+  if (st != MIXDIR_B200_OK) stop("mixdir_b200: %s", mixdir_b200_last_error());
+  std::vector<unsigned char> act(J);
+  for (int j = 0; j < J; j++) act[j] = active[j] ? 1 : 0;
+  NumericVector out(J + 1);
+  st = mixdir_b200_feature_divergence(h, K, lambda.begin(), category_prob_flat.begin(), act.data(),
+                                      ari ? 1 : 0, nullptr, 0, out.begin());
+  mixdir_b200_destroy(h);
+  if (st != MIXDIR_B200_OK) stop("mixdir_b200: %s", mixdir_b200_last_error());
+  return out;  // a caller that loops (find_defining_features) keeps the handle instead: see api.py
+}

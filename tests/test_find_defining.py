@@ -99,3 +99,63 @@ def test_find_defining_features_on_mushroom(mushroom):
     two = api.find_defining_features(res, cols, n_features=2, subsample=np.arange(30))
     assert len(two["features"]) == 2 and np.isscalar(two["quality"])
     assert two["quality"] == pytest.approx(allf["quality"][2], rel=1e-8, abs=1e-12)
+
+
+def test_host_mirror_control_flow_on_cpu(monkeypatch):
+    """The Python twin of find_defining_features (api.py) follows R/predict.R:266-339 step by step;
+    here WITHOUT a GPU: the device pass is replaced by an oracle-backed stand-in, so what is tested
+    is the host logic (removal schedule, ordering, quality bookkeeping, final re-ordering quirk)."""
+    from mixdir_b200 import api
+
+    codes, ncat, K, fit = small_problem(seed=7, N=200, J=9, K=3)
+    J = ncat.size
+    X = po.codes_to_r_matrix(codes)
+
+    class FakeEngine:
+        def __init__(self, c, n, devices=None):
+            assert np.array_equal(c, codes)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            pass
+
+        def feature_divergence(self, K_, lam, U, active, measure, rows=None):
+            Xs = X[rows]
+            cols = [j for j in range(J) if active[j]]
+
+            def pred(cs):
+                Z = np.full_like(Xs, np.nan)
+                Z[:, cs] = Xs[:, cs]
+                return po.predict(Z, ncat, K_, lam, U)[0]
+
+            def q_of(q, p):
+                if measure == "JS":
+                    return float(np.sum(q * (np.log(q) - np.log(p)) + p * (np.log(p) - np.log(q))) / 2)
+                return 1 - float(po.adjusted_rand(np.argmax(q, axis=1), np.argmax(p, axis=1)))
+            p = pred(list(range(J)))
+            out = np.full(J + 1, np.nan)
+            for i in cols:
+                out[i] = q_of(pred([c for c in cols if c != i]), p)
+            out[J] = q_of(pred(cols), p)
+            return out
+
+    monkeypatch.setattr(api, "Engine", FakeEngine)
+    names = [f"f{j}" for j in range(J)]
+    cats = [[str(c) for c in range(1, n + 1)] for n in ncat]
+    obj = {"lambda": fit["lambda_"], "_U_flat": fit["category_prob"], "_names": names,
+           "_categories": cats, "na_handle": "ignore"}
+    Xd = {names[j]: [None if v == 0 else str(v) for v in codes[:, j]] for j in range(J)}
+    sub = np.random.default_rng(4).permutation(codes.shape[0])[:120]
+    for kw in (dict(), dict(n_features=2), dict(n_features=4, step_size=1), dict(exponential_decay=False),
+               dict(measure="ARI"), dict(measure="ARI", n_features=3), dict(exponential_decay=3, step_size=2)):
+        got = api.find_defining_features(obj, Xd, subsample=sub, **kw)
+        feats, quality, _ = po.find_defining_features(X, ncat, K, fit["lambda_"], fit["category_prob"],
+                                                      sub, **kw)
+        assert got["features"] == [names[j] for j in feats], kw
+        np.testing.assert_allclose(got["quality"], quality, rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        api.find_defining_features(obj, Xd, measure="bogus")
+    with pytest.raises(ValueError, match="diverg"):
+        api.find_defining_features(obj, Xd, n_features=J, subsample=sub)
