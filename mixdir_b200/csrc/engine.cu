@@ -1724,55 +1724,71 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     CU_TRY(cudaEventRecord(s.ev_loop0, s.stream));
   }
   std::vector<void*> stat_bufs(h->shards.size());
+  // everything one iteration puts on shard si's stream before / after the all-reduce.  The class
+  // masses of the next iteration go straight back into d_cs_a (k_finalize is the last reader of
+  // the old ones' consequences), so an iteration has the same arguments every time.
+  auto enqueue_front = [&](size_t si, cudaEvent_t e0, cudaEvent_t e1, int* l) -> int {
+    Shard& s = h->shards[si];
+    CU_TRY(cudaSetDevice(s.device));
+    PriorArgs pr = {K, pl.KP, p->dp, p->alpha1, p->alpha2, s.d_cs_a, s.d_prior, s.d_logprior};
+    k_prior<<<1, 256, 0, s.stream>>>(pr);
+    CU_TRY(cudaGetLastError());
+    RET_IF(launch_em(h, s, K, pl, nullptr, true, e0, e1, l));
+    *l += 1;
+    stat_bufs[si] = s.d_stats;
+    return MIXDIR_B200_OK;
+  };
+  auto enqueue_back = [&](size_t si, int it, int* l) -> int {
+    Shard& s = h->shards[si];
+    CU_TRY(cudaSetDevice(s.device));
+    ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
+                    s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
+    k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
+    RET_IF(build_unit_table(s, pl));
+    FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, s.d_stats + tab + pl.KP + 2,
+                       s.d_stats + tab + pl.KP + 3, s.d_pieces, s.d_stats + tab,
+                       s.d_stats + tab + pl.KP, s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior,
+                       s.d_cs_a, s.d_trace, s.d_status};
+    k_finalize<<<1, 256, 0, s.stream>>>(fa);
+    CU_TRY(cudaGetLastError());
+    *l += pl.up.identity ? 2 : 3;
+    if (si == 0)
+      CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(IterStatus), cudaMemcpyDeviceToHost, s.stream));
+    return MIXDIR_B200_OK;
+  };
+  auto read_status = [&](int it) -> int {  // returns 1 when the loop must stop with an error status
+    Shard& s0 = h->shards[0];
+    iters = it + 1;
+    last_elbo = s0.h_status->elbo;
+    warn = s0.h_status->warn;
+    conv = s0.h_status->converged;
+    if (s0.h_status->bad) {  // the upload scan found an invalid code: nothing was computed
+      status = MIXDIR_B200_BAD_ARGUMENT;
+      return 1;
+    }
+    if (s0.h_status->underflow) {
+      status = MIXDIR_B200_UNDERFLOW;
+      return 1;
+    }
+    return 0;
+  };
+
   for (int it = 0; it < p->max_iter && !conv; it++) {
     for (size_t si = 0; si < h->shards.size(); si++) {
-      Shard& s = h->shards[si];
-      CU_TRY(cudaSetDevice(s.device));
-      PriorArgs pr = {K, pl.KP, p->dp, p->alpha1, p->alpha2, s.d_cs_a, s.d_prior, s.d_logprior};
-      k_prior<<<1, 256, 0, s.stream>>>(pr);
-      CU_TRY(cudaGetLastError());
       int l = 0;
-      RET_IF(launch_em(h, s, K, pl, nullptr, true, s.ev_em[2 * it], s.ev_em[2 * it + 1], &l));
-      if (si == 0) launches += 1 + l;
-      stat_bufs[si] = s.d_stats;
+      RET_IF(enqueue_front(si, h->shards[si].ev_em[2 * it], h->shards[si].ev_em[2 * it + 1], &l));
+      if (si == 0) launches += l;
     }
     RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
     for (size_t si = 0; si < h->shards.size(); si++) {
-      Shard& s = h->shards[si];
-      CU_TRY(cudaSetDevice(s.device));
-      ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
-                      s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
-      k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
-      RET_IF(build_unit_table(s, pl));
-      FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, s.d_stats + tab + pl.KP + 2,
-                         s.d_stats + tab + pl.KP + 3, s.d_pieces, s.d_stats + tab,
-                         s.d_stats + tab + pl.KP, s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior,
-                         s.d_cs_b, s.d_trace, s.d_status};
-      k_finalize<<<1, 256, 0, s.stream>>>(fa);
-      CU_TRY(cudaGetLastError());
-      std::swap(s.d_cs_a, s.d_cs_b);
-      if (si == 0) {
-        launches += pl.up.identity ? 2 : 3;
-        CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(IterStatus), cudaMemcpyDeviceToHost, s.stream));
-      }
+      int l = 0;
+      RET_IF(enqueue_back(si, it, &l));
+      if (si == 0) launches += l;
     }
-    {
-      Shard& s0 = h->shards[0];
-      CU_TRY(cudaSetDevice(s0.device));
-      CU_TRY(cudaStreamSynchronize(s0.stream));
-      iters = it + 1;
-      last_elbo = s0.h_status->elbo;
-      warn = s0.h_status->warn;
-      conv = s0.h_status->converged;
-      if (s0.h_status->bad) {  // the upload scan found an invalid code: nothing was computed
-        status = MIXDIR_B200_BAD_ARGUMENT;
-        break;
-      }
-      if (s0.h_status->underflow) {
-        status = MIXDIR_B200_UNDERFLOW;
-        break;
-      }
-    }
+    Shard& s0 = h->shards[0];
+    CU_TRY(cudaSetDevice(s0.device));
+    CU_TRY(cudaStreamSynchronize(s0.stream));
+    if (read_status(it)) break;
   }
   for (auto& s : h->shards) {
     CU_TRY(cudaSetDevice(s.device));

@@ -414,19 +414,20 @@ __global__ void k_finalize(FinalizeArgs a) {
   }
   const double elbo = a.st->termA + tB + tC + tD + a.st->termE + (*a.H) + tG;
   IterStatus* s = a.status;
+  const int it = a.iter;
   int conv = 0, warn = s->warn;
-  if (a.iter != 0 && !isinf(elbo)) {
-    const double diff = elbo - a.trace[a.iter - 1];
+  if (it != 0 && !isinf(elbo)) {
+    const double diff = elbo - a.trace[it - 1];
     if (diff < -a.epsilon) warn |= 1;  // R/mixdir_vi.R:105-108
     if (diff < a.epsilon) conv = 1;    // R/mixdir_vi.R:109
   }
-  a.trace[a.iter] = elbo;
+  a.trace[it] = elbo;
   s->elbo = elbo;
   s->converged = conv;
   s->warn = warn;
   s->underflow = (*a.underflow > 0.0) ? 1 : 0;
   s->bad = (*a.bad > 0.0) ? 1 : 0;
-  s->iter = a.iter;
+  s->iter = it;
 }
 
 // ---------------------------------------------------------------------------

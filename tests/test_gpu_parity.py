@@ -379,3 +379,4 @@ def test_chunked_first_iteration_equals_resident_fit(engine):
         r = eng.fit(K, z0.sum(axis=0), p0, max_iter=3, epsilon=-np.inf, n_cat_bound=ncb)
     assert rel(r["convergence"], ref["convergence"]) < ELBO_RTOL
     assert np.max(np.abs(r["class_prob"] - ref["class_prob"])) < CP_ATOL
+
