@@ -1110,11 +1110,19 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
         layout_units(&u, KC);
         c.FPG = RPW > 2 ? 4 : (u.U / 4 >= 16 ? 4 : 2);
         if (fFPG > 0 && fFPG >= RPW) c.FPG = fFPG;
-        c.W = std::min(16, u.U / c.FPG);
-        if (fW > 0) c.W = std::min(c.W, fW);
-        while (c.W > 1 && ((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) c.W--;
-        if (((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) return (size_t)-1;
-        return UnitSmem(u.srows, KC, c.W, RG, u.WPRu, P).total;
+        // warps: at most one per rotation group; 20 when the tiles of 20 warps still fit (more
+        // read-modify-writes in flight: 13.58 -> 13.09 ms at S4), else 16
+        const int caps[2] = {20, 16};
+        for (int cap : caps) {
+          c.W = std::min(cap, u.U / c.FPG);
+          if (c.W > 8) c.W &= ~3;  // whole warps per scheduler: 17 or 18 warps run slower than 16
+          if (fW > 0) c.W = std::min(c.W, fW);
+          while (c.W > 1 && ((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) c.W--;
+          if (((size_t)c.W * RG * RPW * u.WPRu) % 4 != 0) return (size_t)-1;
+          const size_t tot = UnitSmem(u.srows, KC, c.W, RG, u.WPRu, P).total;
+          if (tot <= (size_t)s.smem_optin || cap == 16) return tot;
+        }
+        return (size_t)-1;
       };
       // Only the number of code words per row (4 elements each) matters: for every word count,
       // fewest first, try the smallest number of pairs that reaches it.
@@ -1146,7 +1154,10 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       const int G = up.U / c.FPG;
       const double ovh = KC == 8 ? 52.0 : (KC == 16 ? 65.0 : 80.0);
       const double rgpen = RG == 8 ? 1.0 : (RG == 4 ? 1.05 : 1.12);
-      const double per_row = P * (up.U * 6.0 / RPW + ovh) * rgpen / used;
+      // fewer warps keep fewer shared-memory requests in flight (sweeps: 8 warps x1.26, 12 x1.07,
+      // 16 x1.0, 20 x0.965)
+      const double wpen = c.W >= 20 ? 0.965 : (c.W >= 16 ? 1.0 : (c.W >= 12 ? 1.07 : (c.W >= 8 ? 1.26 : 1.5)));
+      const double per_row = P * (up.U * 6.0 / RPW + ovh) * rgpen * wpen / used;
       const double per_tile = P * (G * 60.0 + 1500.0) / c.R;
       const double cost = per_row + per_tile;
       if (cost < best_cost) {
