@@ -877,9 +877,9 @@ static bucket_fn pick_bucket(int KC, int CB, int RG) {
   return nullptr;
 }
 
-static units_fn pick_units(int KC, int RG, int FPG);
+static units_fn pick_units(int KC, int RG, int FPG, int W);
 static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
-  if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG);
+  if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG, p.W);
   return p.engine == 3 ? (const void*)pick_bucket(p.KC, h->CB, p.RG)
                        : (const void*)pick_fused(p.KC, h->CB, p.RG);
 }
@@ -1069,9 +1069,10 @@ static void layout_units(UnitPlan* up, int KC) {
     for (int e = 0; e < U; e++) up->eoff_rot[(size_t)r * U + e] = eoff[(e & ~3) | ((e + r) & 3)];
 }
 
-static units_fn pick_units(int KC, int RG, int FPG) {
-#define PICK(kc, rg, fpg) \
-  if (KC == kc && RG == rg && FPG == fpg) return k_em_units<kc, rg, fpg>;
+static units_fn pick_units(int KC, int RG, int FPG, int W) {
+#define PICK(kc, rg, fpg)                   \
+  if (KC == kc && RG == rg && FPG == fpg) \
+    return W > 16 ? k_em_units<kc, rg, fpg, 640> : k_em_units<kc, rg, fpg, 512>;
   PICK(32, 8, 2) PICK(32, 4, 2) PICK(32, 2, 2) PICK(32, 8, 4) PICK(32, 4, 4) PICK(32, 2, 4)
   PICK(16, 8, 2) PICK(16, 4, 2) PICK(16, 2, 2) PICK(16, 8, 4) PICK(16, 4, 4) PICK(16, 2, 4)
   PICK(8, 8, 4) PICK(8, 4, 4) PICK(8, 2, 4)
@@ -1141,7 +1142,7 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       c.engine = 4; c.KC = KC; c.P = P; c.RG = RG; c.KP = P * KC;
       c.R = c.W * RG * RPW;
       c.up = up;
-      if (!pick_units(KC, RG, c.FPG)) continue;
+      if (!pick_units(KC, RG, c.FPG, c.W)) continue;
       c.n_clusters = plan_occupancy(h, s, c);
       if (c.n_clusters < 1) continue;
       // Cost model, in shared-memory cycles per row summed over the CTAs of a cluster and divided
@@ -1590,7 +1591,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
         u.underflow = s.d_underflow;
         u.accumulate = chunked ? 1 : 0;
         u.bad = &s.d_scan->bad;
-        CU_TRY(cudaLaunchKernelEx(&cfg, pick_units(pl.KC, pl.RG, pl.FPG), u));
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_units(pl.KC, pl.RG, pl.FPG, pl.W), u));
       } else if (pl.engine == 3) {
         BucketArgs b;
         b.f = a;

@@ -90,8 +90,10 @@ __device__ __forceinline__ void load_code_words(const uint32_t* p, uint32_t* out
   }
 }
 
-template <int KC, int RG, int FPG>
-__global__ void __launch_bounds__(640, 1) k_em_units(UnitArgs a) {
+// MAXT: launch bound in threads.  512 (16 warps) leaves the compiler 128 registers; 640 (20 warps,
+// <= 102 registers) is used when the tiles of 20 warps fit next to the tables.
+template <int KC, int RG, int FPG, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
   constexpr int RPW = 32 / KC;                       // rows per warp instruction ("slots")
   // (Q = 16/KC table rows sit side by side in a 128-byte shared-memory row; the placement is
   //  done on the host -- engine.cu: layout_units -- and arrives through eoff_rot / slot_of_row)
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(640, 1) k_em_units(UnitArgs a) {
   const int rank = (P > 1) ? (int)cluster.block_rank() : 0;
   const int cluster_id = blockIdx.x / P;
   const int n_clusters = gridDim.x / P;
-  const int W = blockDim.x >> 5;  // up to 20 warps (launch bound 640 threads: <= 102 registers)
+  const int W = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = lane / KC, kc = lane % KC;
   const int kg = rank * KC + kc;  // global (padded) class index of this lane
