@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
       lg[rg] = l;
       ez[rg] = e;
       if (kc < P) {
-        double2* dst = &ex[(size_t)(row_in_tile0 + rg) * P + rank];
+        // layout [source CTA][row]: the owner lanes below read consecutive rows -> no bank conflicts
+        // (row-major [row][P] made 8 lanes hit the same banks at P = 8: 10 % extra wavefronts)
+        double2* dst = &ex[(size_t)rank * R + row_in_tile0 + rg];
         if (P > 1) dst = cluster.map_shared_rank(dst, kc);
         *dst = make_double2(m, live ? s : -s);  // sign bit of the sum carries "not live"
       }
@@ -242,17 +244,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
     uint32_t alive = 0;  // bit rg: some class of this lane's slot has a non-negligible zeta
     double M_o = -INFINITY, f_o = 0.0, logs_o = 0.0;
     if (lane < RW) {
-      const double2* e = ex + (size_t)(wrow0 + lane) * P;
+      const double2* e = ex + wrow0 + lane;  // + p * R
       double M = -INFINITY;
       bool live = false;
       for (int p = 0; p < P; p++) {
-        M = fmax(M, e[p].x);
-        live = live || !signbit(e[p].y);
+        const double2 v = e[(size_t)p * R];
+        M = fmax(M, v.x);
+        live = live || !signbit(v.y);
       }
       double stot = 0.0;
-      for (int p = 0; p < P; p++)
-        if (e[p].x != -INFINITY) stot += fabs(e[p].y) * exp(e[p].x - M);
-      const double mine = e[rank].x;
+      for (int p = 0; p < P; p++) {
+        const double2 v = e[(size_t)p * R];
+        if (v.x != -INFINITY) stot += fabs(v.y) * exp(v.x - M);
+      }
+      const double mine = e[(size_t)rank * R].x;
       f_o = (mine == -INFINITY) ? 0.0 : exp(mine - M) / stot;
       logs_o = log(stot);
       M_o = M;
