@@ -1154,7 +1154,7 @@ static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
       const double used = std::min(1.0, (double)c.n_clusters * P / s.sm_count);
       const int G = up.U / c.FPG;
       const double ovh = KC == 8 ? 52.0 : (KC == 16 ? 65.0 : 80.0);
-      const double rgpen = RG == 8 ? 1.0 : (RG == 4 ? 1.05 : 1.12);
+      const double rgpen = RG == 8 ? 1.0 : (RG == 4 ? 1.08 : 1.30);
       // fewer warps keep fewer shared-memory requests in flight (sweeps: 8 warps x1.26, 12 x1.07,
       // 16 x1.0, 20 x0.965)
       const double wpen = c.W >= 20 ? 0.965 : (c.W >= 16 ? 1.0 : (c.W >= 12 ? 1.07 : (c.W >= 8 ? 1.26 : 1.5)));

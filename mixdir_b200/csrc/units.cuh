@@ -66,7 +66,7 @@ struct UnitSmem {
     off_S = o;     o += (size_t)srows * RS;
     off_tile = o;  o += 2 * R * WPR * 4;
     o = (o + 15) & ~(size_t)15;
-    off_exch = o;  o += 2 * R * P * 16;
+    off_exch = o;  o += 2 * R * 16;  // own (max, sum) per row, double buffered; peers READ it (DSMEM)
     off_ro = o;    o += (size_t)4 * 4 * WPR * 4;
     o = (o + 15) & ~(size_t)15;
     off_red = o;   o += (size_t)(W * KC + W) * 8;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
     }
 
     // ---- soft-max over classes (R/mixdir_vi.R:82), cluster-wide ----
-    double2* ex = exch_s + (size_t)buf * R * P;
+    double2* ex = exch_s + (size_t)buf * R;
     double lg[RG], ez[RG];
 #pragma unroll
     for (int rg = 0; rg < RG; rg++) {
@@ -228,13 +228,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
       const bool live = (__ballot_sync(0xffffffffu, l >= kExpUnderflow) & slot_mask) != 0u;
       lg[rg] = l;
       ez[rg] = e;
-      if (kc < P) {
-        // layout [source CTA][row]: the owner lanes below read consecutive rows -> no bank conflicts
-        // (row-major [row][P] made 8 lanes hit the same banks at P = 8: 10 % extra wavefronts)
-        double2* dst = &ex[(size_t)rank * R + row_in_tile0 + rg];
-        if (P > 1) dst = cluster.map_shared_rank(dst, kc);
-        *dst = make_double2(m, live ? s : -s);  // sign bit of the sum carries "not live"
-      }
+      // this CTA's (max, sum) of the row stays in its own shared memory; after the cluster barrier
+      // the owner lanes of every CTA read the P values through distributed shared memory (an
+      // all-to-all of writes would need P times the buffer: 64 KB at P = 8)
+      if (kc == 0) ex[row_in_tile0 + rg] = make_double2(m, live ? s : -s);  // sign bit: "not live"
     }
     if (P > 1)
       cluster.sync();
@@ -244,20 +241,27 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
     uint32_t alive = 0;  // bit rg: some class of this lane's slot has a non-negligible zeta
     double M_o = -INFINITY, f_o = 0.0, logs_o = 0.0;
     if (lane < RW) {
-      const double2* e = ex + wrow0 + lane;  // + p * R
+      double2* mine_p = ex + wrow0 + lane;
+      double2 v[8];  // P <= 8; the loads are independent, their latencies overlap
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        v[p] = make_double2(-INFINITY, -0.0);
+        if (p < P) v[p] = (P > 1 && p != rank) ? *cluster.map_shared_rank(mine_p, p) : *mine_p;
+      }
       double M = -INFINITY;
       bool live = false;
-      for (int p = 0; p < P; p++) {
-        const double2 v = e[(size_t)p * R];
-        M = fmax(M, v.x);
-        live = live || !signbit(v.y);
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        if (p < P) {
+          M = fmax(M, v[p].x);
+          live = live || !signbit(v[p].y);
+        }
       }
       double stot = 0.0;
-      for (int p = 0; p < P; p++) {
-        const double2 v = e[(size_t)p * R];
-        if (v.x != -INFINITY) stot += fabs(v.y) * exp(v.x - M);
-      }
-      const double mine = e[(size_t)rank * R].x;
+#pragma unroll
+      for (int p = 0; p < 8; p++)
+        if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp(v[p].x - M);
+      const double mine = mine_p->x;
       f_o = (mine == -INFINITY) ? 0.0 : exp(mine - M) / stot;
       logs_o = log(stot);
       M_o = M;
