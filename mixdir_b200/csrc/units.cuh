@@ -5,11 +5,14 @@
 //   phi M-step statistics                    /root/reference/R/mixdir_vi.R:85-91
 //   colSums(zeta), sum_i entrop_zeta(zeta_i) /root/reference/R/mixdir_vi.R:61,101,181-184
 // but built around what the measurements say bounds it: shared-memory wavefronts per code
-// (profiles/README.md: 2 per table gather + 4 per histogram read-modify-write of a 256-byte row,
-// shared-memory pipe 84 % busy).  Three changes against k_em_fused:
+// (profiles/README.md: 2 per table gather + 4 per histogram read-modify-write of a 256-byte row).
+// What differs from k_em_fused:
 //
 //  * ELEMENTS, not features: the row tiles hold packed unit codes (kernels.cuh "Units"), an
-//    element is one feature or a PAIR of features, the tables are the unit tables T2 / S2.
+//    element is one feature or a PAIR of features, the tables are the unit tables T2 / S2; a
+//    feature that holds no NA anywhere has no NA row (smaller pair tables, more pairs fit).
+//  * TILE-TRANSPOSED CODES: [tile][word][row]; the RG rows a lane owns are consecutive, one
+//    128-bit load brings a code word of 4 rows.
 //  * BANK POSITION BY ELEMENT: with KC = 8 classes per CTA a table row is 64 bytes -- half a
 //    128-byte wavefront -- and 4 row slots share a warp instruction.  Which half a slot hits must
 //    not depend on the (random) code, or slots collide in the banks (measured x1.5).  Here a
@@ -18,13 +21,16 @@
 //    (e & ~3) | ((e + s) & 3), so the slots of one instruction always cover every position
 //    equally often: exactly 2 wavefronts per instruction, whatever the codes.
 //  * FINER ROTATION GROUPS + TWO ROWS IN FLIGHT: the M-step rotates warps over groups of FPG
-//    (2 or 4) elements instead of code words, so up to 16 warps stay busy with few elements per
+//    (2 or 4) elements instead of code words, so 16-20 warps stay busy with few elements per
 //    row; each lane keeps the read-modify-writes of two rows in flight and resolves the case
 //    "both rows carry the same code" in registers (the second store then carries both adds).
+//  * SOFT-MAX EXCHANGE BY DSMEM READS: every CTA keeps its own (max, sum) per row; after the
+//    cluster barrier the owner lanes read the peers' values.  The buffer is P times smaller than
+//    an all-to-all of writes, which is what lets 8 row groups per lane fit at P = 8 and 20 warps
+//    at P = 2.
 //
 // Everything else (thread-block clusters splitting the classes, lanes = classes, TMA row tiles,
-// cluster-wide soft-max through distributed shared memory, owner lanes, fixed-order flush)
-// follows fused.cuh.
+// owner lanes, fixed-order flush) follows fused.cuh.
 #pragma once
 
 #include "fused.cuh"
