@@ -367,7 +367,7 @@ def run_ours(args):
                      "shared_memory": shared_memory_roofline(traffic, tm, N, J, K, em_ms_launch, clocks),
                      "note": "shared-memory bound, not HBM bound: see DESIGN.md 4.1 (per code, K fp64 "
                              "table gathers + K fp64 histogram read-modify-writes; the shared-memory "
-                             "pipe runs at 80 % of its wavefront peak, profiles/README.md)"},
+                             "pipe runs at ~81 % of its wavefront peak, profiles/README.md)"},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": f"{args.cpu_rows} rows x {J} features, K={K}, 2 iterations "
                                    f"({cpu_dt:.2f} s/iter), same generator as the GPU workload; "
