@@ -44,15 +44,9 @@ __device__ __forceinline__ int warp_first_argmax(const double* v, int cpl, int K
       bi = k;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) {
-      bv = ov;
-      bi = oi;
-    }
-  }
+  // warp maximum of the values, then the smallest class index among the lanes that hold it
+  const double vmax = warp_max(bv);
+  bi = __reduce_min_sync(0xffffffffu, bv == vmax ? bi : 0x7fffffff);
   return bi == 0x7fffffff ? 0 : bi;
 }
 
@@ -135,9 +129,9 @@ __global__ void __launch_bounds__(256) k_feature_div(FeatureDivArgs a) {
         js = warp_sum(js);
         if (lane == 0) acc[i] += js;
       } else {
-#pragma unroll
-        for (int c = 0; c < 8; c++) q[c] /= sq;
-        const int aq = warp_first_argmax(q, cpl, K, lane);
+        // which.max(q / sum(q)) == which.max(q) for a positive, finite sum; keep R's result (the
+        // first class) when the row's probabilities are all NaN
+        const int aq = (sq > 0.0 && sq < INFINITY) ? warp_first_argmax(q, cpl, K, lane) : 0;
         if (lane == 0) atomicAdd(&a.cont[((size_t)i * K + aq) * K + ap], 1ull);
       }
     }
