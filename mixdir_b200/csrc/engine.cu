@@ -2,10 +2,11 @@
 //
 // Drives the coordinate-ascent loop of mixdir_vi() (/root/reference/R/mixdir_vi.R:58-115)
 // and mixdir_vi_dp() (/root/reference/R/mixdir_vi_dp.R:66-129) entirely on the GPU(s):
-// per iteration  prior step -> fused E+M pass -> deterministic partial reduction ->
-// [NCCL all-reduce of the statistics buffer] -> parameter/ELBO step -> convergence test,
-// with one 32-byte status read-back.  No CPU fallback: every entry point fails with
-// MIXDIR_B200_CUDA_ERROR if no usable device is present.
+// per iteration  fused E+M pass -> [deterministic partial reduction] -> [NCCL all-reduce of the
+// statistics buffer] -> k_iter (parameter/ELBO step, convergence test, next prior).  The host
+// queues iterations ahead and polls a mapped status word; once the device sets `stop` the queued
+// kernels return at once.  No CPU fallback: every entry point fails with MIXDIR_B200_CUDA_ERROR
+// if no usable device is present.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -23,8 +24,8 @@
 #include "../../include/mixdir_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
-#include "bucket.cuh"
 #include "units.cuh"
+#include "iter.cuh"
 #include "predict.cuh"
 #include "features.cuh"
 
@@ -50,6 +51,20 @@ static int fail(int code, const std::string& msg) {
       return fail(MIXDIR_B200_CUDA_ERROR, _b);                                             \
     }                                                                                      \
   } while (0)
+
+// every entry point that touches a device restores the caller's current device on return
+struct DeviceGuard {
+  int dev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      dev = -1;
+      cudaGetLastError();
+    }
+  }
+  ~DeviceGuard() {
+    if (dev >= 0) cudaSetDevice(dev);
+  }
+};
 
 #define RET_IF(expr)                   \
   do {                                 \
@@ -137,7 +152,7 @@ struct UnitPlan {
 };
 
 struct Plan {
-  int engine = 0;  // 1 generic, 2 fused
+  int engine = 0;  // 1 generic, 2 fused, 4 units
   int KP = 0;
   int KC = 0, P = 1, RG = 8, W = 0;
   int FPG = 4;  // engine 4: elements per M-step rotation group
@@ -156,18 +171,23 @@ struct Shard {
   int* d_rowoff = nullptr;
   int* d_rowoff_pad = nullptr;
   int64_t* d_ragoff = nullptr;
-  uint8_t* d_na_row = nullptr;
   nccl::comm_t comm = nullptr;
   bool owns_comm = true;
   int sm_count = 0, smem_optin = 0;
   // workspace (sized for ws_K / ws_KP)
   int ws_K = 0, ws_KP = 0, ws_iter = 0, ws_clusters = 0, ws_ctas = 0;
   double *d_T = nullptr, *d_phi = nullptr, *d_logU = nullptr, *d_stats = nullptr;
-  double *d_logprior = nullptr, *d_cs_a = nullptr, *d_cs_b = nullptr, *d_pieces = nullptr;
+  double *d_logprior = nullptr, *d_cs_a = nullptr, *d_part = nullptr;
   double *d_trace = nullptr, *d_rag_a = nullptr, *d_rag_b = nullptr, *d_lambda = nullptr;
   double *d_lambda_pad = nullptr, *d_prior_out = nullptr;
   double *d_Spart = nullptr, *d_cspart = nullptr, *d_Hpart = nullptr;
-  int *d_perm = nullptr, *d_underflow = nullptr, *d_warn = nullptr;
+  int *d_underflow = nullptr, *d_warn = nullptr;
+  unsigned int* d_ticket = nullptr;
+  // k_iter work list: one block per element (feature or feature pair)
+  int2* d_elem = nullptr;
+  int2* d_erange = nullptr;
+  int n_elem = 0;
+  std::map<const void*, size_t> smem_attr;  // kernels whose dynamic shared memory opt-in is set on this device
   // units (feature pairs): descriptors + packed codes, kept while the plan stays the same
   std::vector<UnitDesc> unit_sig;  // plan the buffers below were built for
   bool unit_valid = false;
@@ -183,9 +203,10 @@ struct Shard {
   int ws_NR2 = 0;
   PriorState* d_prior = nullptr;
   IterStatus* d_status = nullptr;
-  IterStatus* h_status = nullptr;  // pinned
+  IterStatus* h_status = nullptr;  // pinned + mapped: k_iter writes it, the host polls it
   cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
   std::vector<cudaEvent_t> ev_em;
+  std::vector<cudaEvent_t> ev_ring;  // completion of the iterations in flight
   // asynchronous upload: chunks are copied on copy_stream, each followed by an event; the
   // compute stream waits for (and scans) a chunk only when it first needs its rows
   cudaStream_t copy_stream = nullptr;
@@ -215,6 +236,7 @@ struct mixdir_b200_handle {
   int engine_pref = 0;
   int pairing = 1;           // 1: pair features into units where shared memory allows (default)
   bool scan_resolved = false;
+  bool bad = false;  // the upload scan found an invalid code: every later call reports it
   mixdir_b200_timing timing = {};
 };
 
@@ -366,9 +388,9 @@ static void dfree(T*& p) {
 
 static void free_workspace(Shard& s) {
   dfree(s.d_T); dfree(s.d_phi); dfree(s.d_logU); dfree(s.d_stats); dfree(s.d_logprior);
-  dfree(s.d_cs_a); dfree(s.d_cs_b); dfree(s.d_pieces); dfree(s.d_trace); dfree(s.d_rag_a);
+  dfree(s.d_cs_a); dfree(s.d_part); dfree(s.d_trace); dfree(s.d_rag_a);
   dfree(s.d_rag_b); dfree(s.d_lambda); dfree(s.d_lambda_pad); dfree(s.d_prior_out);
-  dfree(s.d_Spart); dfree(s.d_cspart); dfree(s.d_Hpart); dfree(s.d_perm);
+  dfree(s.d_Spart); dfree(s.d_cspart); dfree(s.d_Hpart); dfree(s.d_ticket);
   dfree(s.d_underflow); dfree(s.d_warn); dfree(s.d_prior); dfree(s.d_status); dfree(s.d_T2);
   s.ws_K = s.ws_KP = s.ws_iter = s.ws_clusters = s.ws_ctas = s.ws_NR2 = 0;
 }
@@ -379,10 +401,10 @@ static void free_shard(Shard& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
   free_workspace(s);
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
-  dfree(s.d_ragoff); dfree(s.d_na_row); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
+  dfree(s.d_ragoff); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
   dfree(s.d_na_feat);
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
-  dfree(s.d_slot); dfree(s.d_eoff);
+  dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
   s.unit_valid = false;
   if (s.copy_stream) {
     cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
@@ -397,6 +419,8 @@ static void free_shard(Shard& s) {
   s.h_pin = nullptr;
   for (auto e : s.ev_em) cudaEventDestroy(e);
   s.ev_em.clear();
+  for (auto e : s.ev_ring) cudaEventDestroy(e);
+  s.ev_ring.clear();
   if (s.ev_loop0) cudaEventDestroy(s.ev_loop0);
   if (s.ev_loop1) cudaEventDestroy(s.ev_loop1);
   s.ev_loop0 = s.ev_loop1 = nullptr;
@@ -466,14 +490,10 @@ static int init_shard_static(mixdir_b200_handle* h, Shard& s) {
   RET_IF(dalloc(&s.d_rowoff, J));
   RET_IF(dalloc(&s.d_rowoff_pad, h->rowoff_pad.size()));
   RET_IF(dalloc(&s.d_ragoff, J));
-  RET_IF(dalloc(&s.d_na_row, h->NR));
-  std::vector<uint8_t> na(h->NR, 0);
-  for (int j = 0; j < J; j++) na[h->rowoff[j]] = 1;
   CU_TRY(cudaMemcpy(s.d_ncat, h->ncat.data(), J * sizeof(int), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(s.d_rowoff, h->rowoff.data(), J * sizeof(int), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(s.d_rowoff_pad, h->rowoff_pad.data(), h->rowoff_pad.size() * sizeof(int),
                     cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(s.d_na_row, na.data(), h->NR, cudaMemcpyHostToDevice));
   const size_t bytes = (size_t)(s.n_rows + kRowPad) * h->row_bytes;
   RET_IF(dalloc(&s.d_codes, bytes));
   // Zero what the upload does not write (on the copy stream, i.e. before the copies): the pad
@@ -572,8 +592,14 @@ static int consume_upload(mixdir_b200_handle* h, Shard& s, size_t upto) {
 
 // wait for the whole upload and bring NA count / largest code / validity to the host
 // (collective over ranks in the multi-process flavour)
+static int bad_codes() {
+  return fail(MIXDIR_B200_BAD_ARGUMENT,
+              "a code exceeds its feature's number of categories (or X holds a value that is "
+              "not a positive integer code or NA)");
+}
+
 static int resolve_scan(mixdir_b200_handle* h) {
-  if (h->scan_resolved) return MIXDIR_B200_OK;
+  if (h->scan_resolved) return h->bad ? bad_codes() : MIXDIR_B200_OK;
   int64_t miss = 0;
   int mx = 0, bad = 0;
   for (auto& s : h->shards) {
@@ -624,11 +650,8 @@ static int resolve_scan(mixdir_b200_handle* h) {
   h->n_missing = miss;
   h->max_code = mx;
   h->scan_resolved = true;
-  if (bad)
-    return fail(MIXDIR_B200_BAD_ARGUMENT,
-                "a code exceeds its feature's number of categories (or X holds a value that is "
-                "not a positive integer code or NA)");
-  return MIXDIR_B200_OK;
+  h->bad = bad != 0;
+  return h->bad ? bad_codes() : MIXDIR_B200_OK;
 }
 
 static int make_shards(mixdir_b200_handle* h, int64_t n_rows, int n_devices, const int* device_ids) {
@@ -661,6 +684,7 @@ static int make_shards(mixdir_b200_handle* h, int64_t n_rows, int n_devices, con
 
 extern "C" int mixdir_b200_destroy(mixdir_b200_handle* h) {
   if (!h) return MIXDIR_B200_OK;
+  DeviceGuard guard;
   for (auto& s : h->shards) free_shard(s);
   delete h;
   return MIXDIR_B200_OK;
@@ -672,6 +696,7 @@ extern "C" int mixdir_b200_create(const void* codes, int code_bytes, int64_t n_r
   if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
   *out = nullptr;
   if (n_rows < 0 || (n_rows > 0 && !codes)) return fail(MIXDIR_B200_BAD_ARGUMENT, "codes is NULL");
+  DeviceGuard guard;
   mixdir_b200_handle* h = new mixdir_b200_handle();
   int st = init_geometry(h, code_bytes, n_features, ncat);
   if (st == MIXDIR_B200_OK) st = make_shards(h, n_rows, n_devices, device_ids);
@@ -701,6 +726,7 @@ extern "C" int mixdir_b200_create_from_r_matrix(const double* X, int64_t n_rows,
   int cb = 1;
   for (int j = 0; j < n_features; j++)
     if (ncat[j] > 255) cb = 2;
+  DeviceGuard guard;
   mixdir_b200_handle* h = new mixdir_b200_handle();
   int st = init_geometry(h, cb, n_features, ncat);
   if (st == MIXDIR_B200_OK) st = make_shards(h, n_rows, n_devices, device_ids);
@@ -746,6 +772,7 @@ extern "C" int mixdir_b200_comm_init(int device, int rank, int world, const void
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
     return fail(MIXDIR_B200_CUDA_ERROR, "no CUDA device available (mixdir_b200 has no CPU path)");
   if (device < 0 || device >= count) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad device");
+  DeviceGuard guard;
   mixdir_b200_comm* c = new mixdir_b200_comm();
   c->device = device;
   c->rank = rank;
@@ -784,6 +811,7 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
   if (!comm) return fail(MIXDIR_B200_BAD_ARGUMENT, "comm is NULL");
   if (n_rows_local < 0 || (n_rows_local > 0 && !codes_local))
     return fail(MIXDIR_B200_BAD_ARGUMENT, "codes_local is NULL");
+  DeviceGuard guard;
   mixdir_b200_handle* h = new mixdir_b200_handle();
   h->rank = comm->rank;
   h->world = comm->world;
@@ -813,10 +841,12 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
 
 extern "C" int64_t mixdir_b200_n_rows(const mixdir_b200_handle* h) { return h ? h->n_rows : -1; }
 extern "C" int mixdir_b200_max_code(const mixdir_b200_handle* h) {
+  DeviceGuard guard;
   if (!h || resolve_scan(const_cast<mixdir_b200_handle*>(h)) != MIXDIR_B200_OK) return -1;
   return h->max_code;
 }
 extern "C" int64_t mixdir_b200_n_missing(const mixdir_b200_handle* h) {
+  DeviceGuard guard;
   if (!h || resolve_scan(const_cast<mixdir_b200_handle*>(h)) != MIXDIR_B200_OK) return -1;
   return h->n_missing;
 }
@@ -828,7 +858,7 @@ extern "C" size_t mixdir_b200_ragged_size(int n_features, const int* ncat, int n
   return s * (size_t)n_latent;
 }
 extern "C" int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine) {
-  if (!h || engine < 0 || engine > 4) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (!h || engine < 0 || engine > 5 || engine == 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
   h->engine_pref = engine;
   return MIXDIR_B200_OK;
 }
@@ -848,7 +878,6 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 // per warp (RG), warps (W) such that table + statistics slices fit shared memory
 // ---------------------------------------------------------------------------
 typedef void (*fused_fn)(FusedArgs);
-typedef void (*bucket_fn)(BucketArgs);
 typedef void (*units_fn)(UnitArgs);
 static void layout_units(UnitPlan* up, int KC);
 
@@ -864,31 +893,28 @@ static fused_fn pick_fused(int KC, int CB, int RG) {
   return nullptr;
 }
 
-static bucket_fn pick_bucket(int KC, int CB, int RG) {
-#define PICK(kc, cb, rg) \
-  if (KC == kc && CB == cb && RG == rg) return k_em_bucket<kc, cb, rg>;
-  PICK(32, 1, 8) PICK(32, 1, 6) PICK(32, 1, 4) PICK(32, 1, 2)
-  PICK(16, 1, 8) PICK(16, 1, 6) PICK(16, 1, 4) PICK(16, 1, 2)
-  PICK(8, 1, 4) PICK(8, 1, 2)
-  PICK(32, 2, 8) PICK(32, 2, 6) PICK(32, 2, 4) PICK(32, 2, 2)
-  PICK(16, 2, 8) PICK(16, 2, 6) PICK(16, 2, 4) PICK(16, 2, 2)
-  PICK(8, 2, 4) PICK(8, 2, 2)
-#undef PICK
-  return nullptr;
-}
-
 static units_fn pick_units(int KC, int RG, int FPG, int W);
 static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
   if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG, p.W);
-  return p.engine == 3 ? (const void*)pick_bucket(p.KC, h->CB, p.RG)
-                       : (const void*)pick_fused(p.KC, h->CB, p.RG);
+  return (const void*)pick_fused(p.KC, h->CB, p.RG);
 }
 
-// how many clusters of this plan can be resident at once (0: cannot be scheduled)
-static int plan_occupancy(const mixdir_b200_handle* h, const Shard& s, const Plan& p) {
+// Dynamic shared memory above 48 KB is an opt-in PER DEVICE: set it on the shard's device (which
+// must be current) the first time a kernel is planned or launched there.
+static cudaError_t ensure_smem_attr(Shard& s, const void* fn, size_t bytes) {
+  auto it = s.smem_attr.find(fn);
+  if (it != s.smem_attr.end() && it->second >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) s.smem_attr[fn] = bytes;
+  return e;
+}
+
+// how many clusters of this plan can be resident at once (0: cannot be scheduled);
+// the shard's device must be current
+static int plan_occupancy(const mixdir_b200_handle* h, Shard& s, const Plan& p) {
   const void* fn = plan_fn(h, p);
   if (!fn) return 0;
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  cudaError_t e = ensure_smem_attr(s, fn, p.smem);
   int nclus = 0;
   if (e == cudaSuccess) {
     if (p.P > 1) {
@@ -1083,7 +1109,7 @@ static units_fn pick_units(int KC, int RG, int FPG, int W) {
 // engine 4: k_em_units.  Search (KC, RG, pairs) for the cheapest plan that fits shared memory.
 // MIXDIR_B200_FORCE_PLAN="KC,RG,pairs[,FPG[,W]]" (tuning aid, tools/sweep_plans.py) restricts the
 // search; -1 leaves a field free.
-static bool plan_units(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+static bool plan_units(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   if (h->CB != 1) return false;
   int fKC = -1, fRG = -1, fM = -1, fFPG = -1, fW = -1;
   if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN"))
@@ -1197,7 +1223,7 @@ extern "C" int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pa
 }
 
 // engine 2: k_em_fused (row-owned M-step, read-modify-write per row and unit)
-static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+static bool plan_fused(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   Plan best;
   double best_cost = 1e300;
   const int kcs[3] = {32, 16, 8};
@@ -1254,52 +1280,10 @@ static bool plan_fused(const mixdir_b200_handle* h, const Shard& s, int K, Plan*
   return true;
 }
 
-// engine 3: k_em_bucket (feature-owned M-step over code-sorted tiles)
-static bool plan_bucket(const mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
-  Plan best;
-  double best_cost = 1e300;
-  int cmax = 0;
-  for (int c : h->ncat) cmax = std::max(cmax, c);
-  if (cmax > 4096) return false;  // bucket counters live in shared memory
-  const int entry = h->CB == 1 ? 2 : 4;
-  const int kcs[3] = {32, 16, 8};
-  const int rgs[4] = {8, 6, 4, 2};
-  for (int KC : kcs) {
-    const int RPW = 32 / KC, FPW = 4 / h->CB;
-    const int P = (K + KC - 1) / KC;
-    if (P > 8) continue;
-    const int W = 16;
-    for (int RG : rgs) {
-      const int R = W * RG * RPW;
-      if (RG * RPW > 32) continue;             // one owner lane per row
-      if (h->CB == 1 && R > 256) continue;     // 8-bit row index in the sort entries
-      if (!pick_bucket(KC, h->CB, RG)) continue;
-      BucketSmem L(h->NR, KC, W, RG, h->WPR, FPW, P, h->J, cmax, entry);
-      if (L.total > (size_t)s.smem_optin) continue;
-      const double conflict = KC == 8 ? 1.5 : 1.0;
-      const double cost = P * conflict / RPW + 1e-3 * P + 1e-4 * (8 - RG);
-      if (cost < best_cost) {
-        Plan c;
-        c.engine = 3; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC;
-        c.smem = L.total; c.R = R;
-        identity_units(h, &c.up);
-        c.n_clusters = plan_occupancy(h, s, c);
-        if (c.n_clusters < 1) continue;
-        best_cost = cost;
-        best = c;
-      }
-      break;  // largest RG that fits for this KC
-    }
-  }
-  if (best.engine != 3) return false;
-  *out = best;
-  return true;
-}
-
-// engine_pref: 0 automatic (fused, else bucket, else generic), 1 generic, 2 fused, 3 bucket.
-// The bucket kernel moves fewer shared-memory bytes but executes twice the instructions and
-// measured slower (profiles/README.md), so it is only a fallback in automatic mode.
-static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) {
+// engine_pref: 0 automatic (unit kernel, else fused, else generic), 1 generic, 2 fused, 4 units.
+// Planning happens on the first shard's device (all shards of a handle are the same GPU model).
+static int plan_engine(mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
+  CU_TRY(cudaSetDevice(s.device));
   const int pref = h->engine_pref;
   if ((pref == 0 || pref == 4) && plan_units(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 4)
@@ -1308,9 +1292,6 @@ static int plan_engine(mixdir_b200_handle* h, const Shard& s, int K, Plan* out) 
   if ((pref == 0 || pref == 2) && plan_fused(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 2)
     return fail(MIXDIR_B200_BAD_ARGUMENT, "fused kernel does not fit this problem shape (K, sum C_j)");
-  if ((pref == 0 || pref == 3) && plan_bucket(h, s, K, out)) return MIXDIR_B200_OK;
-  if (pref == 3)
-    return fail(MIXDIR_B200_BAD_ARGUMENT, "bucket kernel does not fit this problem shape (K, sum C_j)");
   Plan g;
   g.engine = 1;
   g.KP = (K + 7) & ~7;
@@ -1337,15 +1318,14 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   RET_IF(dalloc(&s.d_stats, tab + KP + 4));
   RET_IF(dalloc(&s.d_logprior, KP));
   RET_IF(dalloc(&s.d_cs_a, kMaxClasses));
-  RET_IF(dalloc(&s.d_cs_b, kMaxClasses));
-  RET_IF(dalloc(&s.d_pieces, (size_t)h->J * K * 3));
+  RET_IF(dalloc(&s.d_part, (size_t)h->J * 3));
   RET_IF(dalloc(&s.d_trace, std::max(max_iter, 1)));
   RET_IF(dalloc(&s.d_rag_a, rag));
   RET_IF(dalloc(&s.d_rag_b, rag));
   RET_IF(dalloc(&s.d_lambda, K));
   RET_IF(dalloc(&s.d_lambda_pad, KP));
   RET_IF(dalloc(&s.d_prior_out, 2 * K));
-  RET_IF(dalloc(&s.d_perm, K));
+  RET_IF(dalloc(&s.d_ticket, 1));
   RET_IF(dalloc(&s.d_underflow, 1));
   RET_IF(dalloc(&s.d_warn, 1));
   RET_IF(dalloc(&s.d_prior, 1));
@@ -1358,6 +1338,9 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   CU_TRY(cudaMemsetAsync(s.d_T, 0, tab * sizeof(double), s.stream));
   CU_TRY(cudaMemsetAsync(s.d_phi, 0, tab * sizeof(double), s.stream));
   CU_TRY(cudaMemsetAsync(s.d_logU, 0, tab * sizeof(double), s.stream));
+  CU_TRY(cudaMemsetAsync(s.d_ticket, 0, sizeof(unsigned int), s.stream));
+  CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
+  CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
   s.ws_K = K;
   s.ws_KP = KP;
   s.ws_iter = std::max(max_iter, 1);
@@ -1415,7 +1398,8 @@ static size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
 static size_t unit_stage_bytes(const UnitPlan& up) {
   return pad8(up.desc.size() * sizeof(UnitDesc)) + pad8(up.gbase.size() * sizeof(int)) +
          pad8(up.t2src.size() * sizeof(int2)) + pad8(up.marg.size() * sizeof(MargDesc)) +
-         pad8(up.slot.size() * sizeof(int)) + pad8(up.eoff_rot.size() * sizeof(int)) + 8 * 64;
+         pad8(up.slot.size() * sizeof(int)) + pad8(up.eoff_rot.size() * sizeof(int)) +
+         2 * pad8(up.desc.size() * sizeof(int2)) + 10 * 64;
 }
 
 template <typename T>
@@ -1440,8 +1424,25 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
     return MIXDIR_B200_OK;
   s.unit_valid = false;
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
-  dfree(s.d_slot); dfree(s.d_eoff);
+  dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
   s.packed_rows = 0;
+  {  // k_iter's work list: the real elements (feature, or the two features of a pair)
+    std::vector<int2> elem, erange;
+    for (int e = 0; e < up.U; e++) {
+      const UnitDesc& d = up.desc[e];
+      if (d.off_a < 0) continue;
+      if (up.identity) {
+        elem.push_back(make_int2(d.off_a / h->CB, -1));
+        erange.push_back(make_int2(0, 0));
+      } else {
+        elem.push_back(make_int2(d.off_a, d.off_b < 0 ? -1 : d.off_b));
+        erange.push_back(make_int2(up.gbase[e], up.erows[e]));
+      }
+    }
+    s.n_elem = (int)elem.size();
+    RET_IF(send_vec(s, &s.d_elem, elem));
+    RET_IF(send_vec(s, &s.d_erange, erange));
+  }
   RET_IF(send_vec(s, &s.d_udesc, up.desc));
   RET_IF(send_vec(s, &s.d_ugbase, up.gbase));
   RET_IF(send_vec(s, &s.d_marg, up.marg));
@@ -1501,7 +1502,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
   const UnitPlan& up = pl.up;
   const uint8_t* ucodes = up.identity ? s.d_codes : s.d_ucodes;
   const size_t urow_bytes = up.identity ? (size_t)h->row_bytes : (size_t)up.WPRu * 4;
-  CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
+  const int* stop = &s.d_status->stop;
   // row ranges of this pass: one per pending upload chunk, else the whole shard
   std::vector<std::pair<int64_t, int64_t>> ranges;
   std::vector<size_t> range_chunk;  // upload chunk to consume before range i (or SIZE_MAX)
@@ -1558,6 +1559,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       a.underflow = s.d_underflow;
       a.accumulate = chunked ? 1 : 0;
       a.bad = &s.d_scan->bad;
+      a.stop = stop;
+      CU_TRY(ensure_smem_attr(s, plan_fn(h, pl), pl.smem));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(nclus * pl.P);
       cfg.blockDim = dim3(32 * pl.W);
@@ -1591,14 +1594,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
         u.underflow = s.d_underflow;
         u.accumulate = chunked ? 1 : 0;
         u.bad = &s.d_scan->bad;
+        u.stop = stop;
         CU_TRY(cudaLaunchKernelEx(&cfg, pick_units(pl.KC, pl.RG, pl.FPG, pl.W), u));
-      } else if (pl.engine == 3) {
-        BucketArgs b;
-        b.f = a;
-        b.J = h->J;
-        b.ncat = s.d_ncat;
-        b.rowoff = s.d_rowoff;
-        CU_TRY(cudaLaunchKernelEx(&cfg, pick_bucket(pl.KC, h->CB, pl.RG), b));
       } else {
         CU_TRY(cudaLaunchKernelEx(&cfg, pick_fused(pl.KC, h->CB, pl.RG), a));
       }
@@ -1618,8 +1615,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
     r.scan = s.d_scan;
     r.marg = s.d_marg;
     r.stats = s.d_stats;
-    const int rgrid = (int)std::min<size_t>((tab + 255) / 256, (size_t)s.sm_count * 4);
-    k_reduce_units<<<rgrid, 256, 0, s.stream>>>(r);
+    r.stop = stop;
+    k_reduce_units<<<dim3(h->NR, (pl.KP + 31) / 32), 256, 0, s.stream>>>(r);
     CU_TRY(cudaGetLastError());
     *launches += 1;
     h->timing.grid_ctas = max_clus * pl.P;
@@ -1648,6 +1645,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       g.zeta_row0 = r0;
       g.do_scatter = scatter ? 1 : 0;
       g.bad = &s.d_scan->bad;
+      g.stop = stop;
       const int grid = s.sm_count * 8;
       if (h->CB == 1)
         k_em_generic<1><<<grid, 256, 0, s.stream>>>(g);
@@ -1657,7 +1655,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       *launches += 1;
     }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
-    k_tail_to_stats<<<1, 1, 0, s.stream>>>(s.d_underflow, s.d_scan, s.d_stats + tab + pl.KP + 1);
+    k_tail_to_stats<<<1, 1, 0, s.stream>>>(s.d_underflow, s.d_scan, s.d_stats + tab + pl.KP + 1, stop);
     CU_TRY(cudaGetLastError());
     *launches += 1;
   }
@@ -1685,6 +1683,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
                                int* warn_flags) {
   RET_IF(check_fit_args(h, p));
   if (!colsum_init || !phi_init) return fail(MIXDIR_B200_BAD_ARGUMENT, "colsum_init / phi_init is NULL");
+  DeviceGuard guard;
   const int K = p->n_latent, J = h->J;
   // the table needs n_cat = max(X) (R/mixdir_vi.R:8) before the first pass: when the caller
   // does not pass it, wait for the upload scan (no upload/compute overlap in that case)
@@ -1705,6 +1704,20 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   h->timing.unit_table_rows = pl.up.NR2;
 
   // ---- initial state on every shard: class masses + table from phi_init ----
+  auto iter_args = [&](Shard& s, int mode, bool poll) -> IterArgs {
+    IterArgs ia;
+    ia.J = J; ia.K = K; ia.KP = pl.KP; ia.dp = p->dp; ia.mode = mode;
+    ia.n_cat_bound = n_cat_bound; ia.NR = h->NR; ia.NR2 = pl.up.NR2; ia.stats_fixed = 0;
+    ia.beta = p->beta; ia.a1 = p->alpha1; ia.a2 = p->alpha2; ia.epsilon = p->epsilon;
+    ia.ncat = s.d_ncat; ia.rowoff = s.d_rowoff; ia.elem = s.d_elem; ia.erange = s.d_erange;
+    ia.t2src = pl.up.identity ? nullptr : s.d_t2src;
+    ia.stats = s.d_stats; ia.phi = s.d_phi; ia.T = s.d_T; ia.T2 = s.d_T2; ia.part = s.d_part;
+    ia.ticket = s.d_ticket; ia.underflow_flag = s.d_underflow; ia.st = s.d_prior;
+    ia.logprior = s.d_logprior; ia.cs_cur = s.d_cs_a; ia.trace = s.d_trace; ia.status = s.d_status;
+    ia.status_host = nullptr;
+    if (poll) cudaHostGetDevicePointer((void**)&ia.status_host, s.h_status, 0);
+    return ia;
+  };
   for (auto& s : h->shards) {
     RET_IF(ensure_workspace(h, s, K, pl, p->max_iter));
     RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096 + unit_stage_bytes(pl.up)));
@@ -1719,16 +1732,20 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     RET_IF(pin_send(s, s.d_rag_a, phi_init, rag * sizeof(double)));
     CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
     CU_TRY(cudaMemsetAsync(s.d_warn, 0, sizeof(int), s.stream));
+    CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
+    memset(s.h_status, 0, sizeof(IterStatus));
     ScatterRagArgs ra = {J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_phi, 0, 0.0};
     k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
-    ParamArgs pa = {J, K, pl.KP, p->dp, 0, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
-                    nullptr, nullptr, s.d_phi, s.d_T, nullptr, s.d_perm};
-    k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
+    // table T (+ unit table T2) from phi_init, prior of the first iteration from colsum_init
+    k_iter<<<s.n_elem, kIterThreads, 0, s.stream>>>(iter_args(s, 0, false));
     CU_TRY(cudaGetLastError());
-    RET_IF(build_unit_table(s, pl));
   }
 
   // ---- the coordinate-ascent loop (R/mixdir_vi.R:58-115) ----
+  // The host never waits for an iteration: it keeps up to kDepth iterations queued and reads the
+  // status word k_iter mirrors into mapped page-locked memory.  Once the device has set `stop`
+  // (converged / underflow / invalid codes) the kernels still in the queue return at once.
+  constexpr int kDepth = 8;
   int iters = 0, conv = 0, warn = 0, status = MIXDIR_B200_OK, launches = 0;
   double last_elbo = NAN;
   for (auto& s : h->shards) {
@@ -1736,71 +1753,38 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     CU_TRY(cudaEventRecord(s.ev_loop0, s.stream));
   }
   std::vector<void*> stat_bufs(h->shards.size());
-  // everything one iteration puts on shard si's stream before / after the all-reduce.  The class
-  // masses of the next iteration go straight back into d_cs_a (k_finalize is the last reader of
-  // the old ones' consequences), so an iteration has the same arguments every time.
-  auto enqueue_front = [&](size_t si, cudaEvent_t e0, cudaEvent_t e1, int* l) -> int {
-    Shard& s = h->shards[si];
-    CU_TRY(cudaSetDevice(s.device));
-    PriorArgs pr = {K, pl.KP, p->dp, p->alpha1, p->alpha2, s.d_cs_a, s.d_prior, s.d_logprior};
-    k_prior<<<1, 256, 0, s.stream>>>(pr);
-    CU_TRY(cudaGetLastError());
-    RET_IF(launch_em(h, s, K, pl, nullptr, true, e0, e1, l));
-    *l += 1;
-    stat_bufs[si] = s.d_stats;
-    return MIXDIR_B200_OK;
-  };
-  auto enqueue_back = [&](size_t si, int it, int* l) -> int {
-    Shard& s = h->shards[si];
-    CU_TRY(cudaSetDevice(s.device));
-    ParamArgs pa = {J, K, pl.KP, p->dp, 1, n_cat_bound, p->beta, s.d_ncat, s.d_rowoff,
-                    s.d_stats, s.d_stats + tab, s.d_phi, s.d_T, s.d_pieces, s.d_perm};
-    k_param<<<jk_grid, 128, 0, s.stream>>>(pa);
-    RET_IF(build_unit_table(s, pl));
-    FinalizeArgs fa = {J, K, pl.KP, p->dp, it, p->epsilon, s.d_stats + tab + pl.KP + 2,
-                       s.d_stats + tab + pl.KP + 3, s.d_pieces, s.d_stats + tab,
-                       s.d_stats + tab + pl.KP, s.d_stats + tab + pl.KP + 1, s.d_perm, s.d_prior,
-                       s.d_cs_a, s.d_trace, s.d_status};
-    k_finalize<<<1, 256, 0, s.stream>>>(fa);
-    CU_TRY(cudaGetLastError());
-    *l += pl.up.identity ? 2 : 3;
-    if (si == 0)
-      CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(IterStatus), cudaMemcpyDeviceToHost, s.stream));
-    return MIXDIR_B200_OK;
-  };
-  auto read_status = [&](int it) -> int {  // returns 1 when the loop must stop with an error status
-    Shard& s0 = h->shards[0];
-    iters = it + 1;
-    last_elbo = s0.h_status->elbo;
-    warn = s0.h_status->warn;
-    conv = s0.h_status->converged;
-    if (s0.h_status->bad) {  // the upload scan found an invalid code: nothing was computed
-      status = MIXDIR_B200_BAD_ARGUMENT;
-      return 1;
+  Shard& s0 = h->shards[0];
+  while ((int)s0.ev_ring.size() < kDepth) {
+    cudaEvent_t e;
+    CU_TRY(cudaSetDevice(s0.device));
+    CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s0.ev_ring.push_back(e);
+  }
+  std::vector<int> iter_launches;
+  for (int it = 0; it < p->max_iter; it++) {
+    if (it >= kDepth) {
+      CU_TRY(cudaEventSynchronize(s0.ev_ring[it % kDepth]));  // iteration it - kDepth is done
+      if (((volatile IterStatus*)s0.h_status)->stop) break;
     }
-    if (s0.h_status->underflow) {
-      status = MIXDIR_B200_UNDERFLOW;
-      return 1;
-    }
-    return 0;
-  };
-
-  for (int it = 0; it < p->max_iter && !conv; it++) {
+    int l0 = 0;
     for (size_t si = 0; si < h->shards.size(); si++) {
+      Shard& s = h->shards[si];
       int l = 0;
-      RET_IF(enqueue_front(si, h->shards[si].ev_em[2 * it], h->shards[si].ev_em[2 * it + 1], &l));
-      if (si == 0) launches += l;
+      RET_IF(launch_em(h, s, K, pl, nullptr, true, s.ev_em[2 * it], s.ev_em[2 * it + 1], &l));
+      stat_bufs[si] = s.d_stats;
+      if (si == 0) l0 += l;
     }
     RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
     for (size_t si = 0; si < h->shards.size(); si++) {
-      int l = 0;
-      RET_IF(enqueue_back(si, it, &l));
-      if (si == 0) launches += l;
+      Shard& s = h->shards[si];
+      CU_TRY(cudaSetDevice(s.device));
+      k_iter<<<s.n_elem, kIterThreads, 0, s.stream>>>(iter_args(s, 1, si == 0));
+      CU_TRY(cudaGetLastError());
+      if (si == 0) l0 += 1;
     }
-    Shard& s0 = h->shards[0];
     CU_TRY(cudaSetDevice(s0.device));
-    CU_TRY(cudaStreamSynchronize(s0.stream));
-    if (read_status(it)) break;
+    CU_TRY(cudaEventRecord(s0.ev_ring[it % kDepth], s0.stream));
+    iter_launches.push_back(l0);
   }
   for (auto& s : h->shards) {
     CU_TRY(cudaSetDevice(s.device));
@@ -1811,8 +1795,15 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     CU_TRY(cudaStreamSynchronize(s.stream));
   }
   {
-    Shard& s0 = h->shards[0];
     CU_TRY(cudaSetDevice(s0.device));
+    const IterStatus fin = *s0.h_status;
+    iters = fin.iter;
+    conv = fin.converged;
+    warn = fin.warn;
+    if (iters > 0) last_elbo = fin.elbo;
+    if (fin.bad) status = MIXDIR_B200_BAD_ARGUMENT;  // the upload scan found an invalid code
+    else if (fin.underflow) status = MIXDIR_B200_UNDERFLOW;
+    for (int it = 0; it < iters; it++) launches += iter_launches[it];
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, s0.ev_loop0, s0.ev_loop1));
     h->timing.fit_loop_ms = ms;
@@ -1833,8 +1824,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   if (elbo) *elbo = last_elbo;
   if (status == MIXDIR_B200_BAD_ARGUMENT) {
     if (warn_flags) *warn_flags = 0;
-    return fail(status, "a code exceeds its feature's number of categories (or X holds a value "
-                        "that is not a positive integer code or NA)");
+    return bad_codes();
   }
   if (status != MIXDIR_B200_OK) {
     if (warn_flags) *warn_flags = warn;
@@ -1941,6 +1931,7 @@ extern "C" int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const do
   if (!h || !lambda || !category_prob) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
+  DeviceGuard guard;
   RET_IF(resolve_scan(h));
   Plan pl;
   pl.engine = 1;
@@ -2003,6 +1994,7 @@ extern "C" int mixdir_b200_feature_divergence(mixdir_b200_handle* h, int n_laten
   const size_t ncont = (size_t)(J + 1) * K * K;
   if (measure == 1 && ncont > ((size_t)1 << 27))
     return fail(MIXDIR_B200_BAD_ARGUMENT, "ARI contingency tables too large ((J+1) * K^2 > 2^27)");
+  DeviceGuard guard;
   RET_IF(resolve_scan(h));
   Plan pl;
   pl.engine = 1;
@@ -2100,7 +2092,8 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   if (!h || !log_prior || !table) return fail(MIXDIR_B200_BAD_ARGUMENT, "NULL argument");
   const int K = n_latent;
   if (K < 1 || K > kMaxClasses) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_latent must be in 1..256");
-  if (engine < 0 || engine > 4) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  if (engine < 0 || engine > 5 || engine == 3) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad engine");
+  DeviceGuard guard;
   RET_IF(resolve_scan(h));
   const int keep = h->engine_pref;
   if (engine) h->engine_pref = engine;
@@ -2122,6 +2115,8 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     RET_IF(ensure_units(h, s, pl));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
+    CU_TRY(cudaMemsetAsync(s.d_underflow, 0, sizeof(int), s.stream));
     ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, s.d_rag_a, s.d_T, 0, 0.0};
     k_ragged_to_table<<<jk_grid, 128, 0, s.stream>>>(ra);
     CU_TRY(cudaGetLastError());

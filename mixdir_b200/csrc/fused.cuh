@@ -50,6 +50,7 @@ struct FusedArgs {
   int* underflow;
   int accumulate;         // 1: add to the partial buffers (chunked first iteration), 0: overwrite
   const int* bad;         // invalid codes seen by the upload scan: do nothing
+  const int* stop;        // fit already over (converged / error): do nothing
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(512, 1) k_em_fused(FusedArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
   const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
-  if (*a.bad) return;  // uniform over the grid: a code above C_j would index outside the tables
+  // uniform over the grid: a code above C_j would index outside the tables / the fit is over
+  if (*a.bad || *a.stop) return;
 
   // ---- prologue: barriers, first tile in flight, tables into shared memory ----
   if (threadIdx.x == 0) {

@@ -177,258 +177,15 @@ struct PriorState {
   double termE;                // entrop_omega (R/mixdir_vi.R:177)     | dp_entrop_v (dp.R:214)
 };
 
-struct PriorArgs {
-  int K, KP, dp;
-  double a1, a2;
-  const double* cs;   // [K] class masses colSums(zeta) (R/mixdir_vi.R:61)
-  PriorState* st;
-  double* logprior;   // [KP] psi-part of the logit, WITHOUT the "-1" (mixdir_impl.cpp:83,148)
-};
-
-__global__ void k_prior(PriorArgs a) {
-  __shared__ double lg1[kMaxClasses], lg2[kMaxClasses], lg12[kMaxClasses], d1[kMaxClasses],
-      d2[kMaxClasses], d12[kMaxClasses];
-  const int K = a.K;
-  PriorState* st = a.st;
-  if (!a.dp) {
-    // omega <- alpha + colSums(zeta)   (R/mixdir_vi.R:61)
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const double om = a.a1 + a.cs[k];
-      st->omega[k] = om;
-      d1[k] = dev_digamma(om);
-      lg1[k] = lgamma(om);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double so = 0;
-      for (int k = 0; k < K; k++) so += st->omega[k];
-      const double dso = dev_digamma(so);  // mixdir_impl.cpp:59
-      double sA = 0, sl = 0, sE = 0;
-      for (int k = 0; k < K; k++) {
-        const double e = d1[k] - dso;
-        st->e1[k] = e;
-        a.logprior[k] = e;
-        sA += (a.a1 - 1.0) * e;
-        sl += lg1[k];
-        sE += (st->omega[k] - 1.0) * e;
-      }
-      for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
-      st->termA = lgamma(K * a.a1) - K * lgamma(a.a1) + sA;  // R/mixdir_vi.R:164-166
-      st->termE = -lgamma(so) + sl - sE;                      // R/mixdir_vi.R:177-179
-    }
-  } else {
-    // kappa1 <- a1 + colSums(zeta); kappa2_k <- a2 + sum_{l>k} colSums(zeta)_l  (dp.R:68-71)
-    if (threadIdx.x == 0) {
-      double tail = 0;
-      for (int k = K - 1; k >= 0; k--) {
-        st->kappa2[k] = a.a2 + tail;
-        tail += a.cs[k];
-      }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const double k1 = a.a1 + a.cs[k];
-      const double k2 = st->kappa2[k];
-      st->omega[k] = k1;
-      d1[k] = dev_digamma(k1);
-      d2[k] = dev_digamma(k2);
-      d12[k] = dev_digamma(k1 + k2);
-      lg1[k] = lgamma(k1);
-      lg2[k] = lgamma(k2);
-      lg12[k] = lgamma(k1 + k2);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double skp = 0, sA = 0, sE = 0;
-      for (int k = 0; k < K; k++) {
-        const double k1 = st->omega[k], k2 = st->kappa2[k];
-        const double e1 = d1[k] - d12[k];
-        const double e2 = d2[k] - d12[k];
-        st->e1[k] = e1;
-        st->e2[k] = e2;
-        a.logprior[k] = e1 + skp;  // mixdir_impl.cpp:131-138,148
-        skp += e2;
-        sA += (a.a1 - 1.0) * e1 + (a.a2 - 1.0) * e2;  // dp.R:196-200
-        sE += lg1[k] + lg2[k] - lg12[k] - (k1 - 1.0) * d1[k] - (k2 - 1.0) * d2[k] +
-              (k1 + k2 - 2.0) * d12[k];  // dp.R:214-221
-      }
-      for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
-      st->termA = sA;
-      st->termE = sE;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// parameter step over (feature, class) pairs: [DP: re-order classes by mass]
-// -> phi = S + beta -> T = psi(phi) - psi(sum phi) -> per-(j,k) ELBO pieces.
-// ---------------------------------------------------------------------------
-struct ParamArgs {
-  int J, K, KP, dp;
-  int mode;           // 0: phi given (initial table); 1: phi from S (+ ELBO pieces)
-  int n_cat_bound;    // loop bound of the digamma-sum (mixdir_impl.cpp:65 quirk)
-  double beta;
-  const int* ncat;    // [J]
-  const int* rowoff;  // [J]
-  const double* S;    // [NR][KP]   (mode 1)
-  const double* cs;   // [KP] new class masses, unpermuted (mode 1)
-  double* phi;        // [NR][KP]
-  double* T;          // [NR][KP]
-  double* pieces;     // [J*K][3]: C-term, D-term, G-term per (j,k) (mode 1)
-  int* perm;          // [K] new class -> old class (written by block 0)
-};
-
-__global__ void k_param(ParamArgs a) {
-  __shared__ int perm[kMaxClasses];
-  const int K = a.K;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    if (a.dp && a.mode == 1) {
-      // zeta <- zeta[, order(-colSums(zeta))]  (R/mixdir_vi_dp.R:97): stable, descending.
-      const double c = a.cs[k];
-      int rank = 0;
-      for (int l = 0; l < K; l++) {
-        const double cl = a.cs[l];
-        rank += (cl > c) || (cl == c && l < k);
-      }
-      perm[rank] = k;
-    } else {
-      perm[k] = k;
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0)
-    for (int k = threadIdx.x; k < K; k += blockDim.x) a.perm[k] = perm[k];
-
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= a.J * K) return;
-  const int j = id / K, k = id - j * K;
-  const int C = a.ncat[j];
-  const size_t g0 = (size_t)a.rowoff[j];
-  const int old = perm[k];
-  const int KP = a.KP;
-
-  double sum_all = 0, sum_bound = 0;
-  for (int r = 0; r < C; r++) {
-    const size_t g = g0 + 1 + r;
-    // phi[[j]][[k]][r] <- sum(zeta[,k] * (X[,j]==r), na.rm=TRUE) + beta  (R/mixdir_vi.R:88)
-    const double ph = a.mode == 1 ? a.S[g * KP + old] + a.beta : a.phi[g * KP + k];
-    a.phi[g * KP + k] = ph;
-    sum_all += ph;
-    if (r < a.n_cat_bound) sum_bound += ph;
-  }
-  const double ds_bound = dev_digamma(sum_bound);  // mixdir_impl.cpp:61-72
-  const double ds_all = dev_digamma(sum_all);      // R-level digamma(sum(phi_jk))
-  double cpart = 0, dpart = 0, lgs = 0, gpart = 0;
-  for (int r = 0; r < C; r++) {
-    const size_t g = g0 + 1 + r;
-    const double ph = a.phi[g * KP + k];
-    const double dg = dev_digamma(ph);
-    const double t = dg - ds_bound;  // mixdir_impl.cpp:80
-    a.T[g * KP + k] = t;
-    if (a.mode == 1) {
-      cpart += (a.beta - 1.0) * (dg - ds_all);  // expec_log_ujk, R/mixdir_vi.R:172-174
-      dpart += a.S[g * KP + old] * t;           // expec_log_x_cpp collapsed
-      lgs += lgamma(ph);
-      gpart += (ph - 1.0) * (dg - ds_all);      // entrop_phi, R/mixdir_vi.R:190-192
-    }
-  }
-  a.T[g0 * KP + k] = 0.0;  // NA row
-  if (a.mode == 1) {
-    double* p = a.pieces + (size_t)id * 3;
-    p[0] = lgamma(C * a.beta) - C * lgamma(a.beta) + cpart;
-    p[1] = dpart;
-    p[2] = -lgamma(sum_all) + lgs - gpart;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// finalize: deterministic reduction of the (j,k) pieces, ELBO assembly
-// (R/mixdir_vi.R:94-102), convergence test (R/mixdir_vi.R:105-109), and the
-// class masses carried to the next iteration (permuted for DP).  One block.
-// ---------------------------------------------------------------------------
 struct IterStatus {
   double elbo;
   int converged;
   int warn;
   int underflow;
-  int iter;  // 0-based index of the iteration just finished
+  int iter;  // iterations finished so far
   int bad;   // some code exceeded its feature's number of categories (any rank)
-  int pad_;
+  int stop;  // converged, underflow or invalid codes: every later kernel of the fit returns at once
 };
-
-struct FinalizeArgs {
-  int J, K, KP, dp, iter;
-  double epsilon;
-  const double* n_missing;  // nNA (all ranks): "+1 per NA cell per class", mixdir_impl.cpp:29-30
-  const double* bad;        // > 0 if any rank saw an invalid code
-  const double* pieces;     // [J*K][3]
-  const double* cs;         // [KP] new class masses (unpermuted)
-  const double* H;          // entropy sum (R/mixdir_vi.R:181-184)
-  const double* underflow;  // > 0 if any rank saw an underflowing row
-  const int* perm;          // [K]
-  const PriorState* st;
-  double* cs_next;          // [K] permuted class masses -> next k_prior
-  double* trace;            // [max_iter]
-  IterStatus* status;
-};
-
-__global__ void k_finalize(FinalizeArgs a) {
-  __shared__ double red[3][256];
-  const int K = a.K;
-  const int n = a.J * a.K;
-  double s0 = 0, s1 = 0, s2 = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s0 += a.pieces[(size_t)i * 3 + 0];
-    s1 += a.pieces[(size_t)i * 3 + 1];
-    s2 += a.pieces[(size_t)i * 3 + 2];
-  }
-  red[0][threadIdx.x] = s0;
-  red[1][threadIdx.x] = s1;
-  red[2][threadIdx.x] = s2;
-  __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + o];
-      red[1][threadIdx.x] += red[1][threadIdx.x + o];
-      red[2][threadIdx.x] += red[2][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x != 0) return;
-  const double tC = red[0][0], tD = red[1][0] + (double)K * (*a.n_missing), tG = red[2][0];
-  double tB = 0;
-  if (!a.dp) {
-    for (int k = 0; k < K; k++) {
-      const double c = a.cs[a.perm[k]];
-      a.cs_next[k] = c;
-      tB += c * a.st->e1[k];  // expec_log_zi summed over rows, R/mixdir_vi.R:168-170
-    }
-  } else {
-    double tail = 0;  // sum_{l>k} of the permuted class masses
-    for (int k = K - 1; k >= 0; k--) {
-      const double c = a.cs[a.perm[k]];
-      a.cs_next[k] = c;
-      tB += tail * a.st->e2[k] + c * a.st->e1[k];  // dp_expec_log_zi, dp.R:202-211
-      tail += c;
-    }
-  }
-  const double elbo = a.st->termA + tB + tC + tD + a.st->termE + (*a.H) + tG;
-  IterStatus* s = a.status;
-  const int it = a.iter;
-  int conv = 0, warn = s->warn;
-  if (it != 0 && !isinf(elbo)) {
-    const double diff = elbo - a.trace[it - 1];
-    if (diff < -a.epsilon) warn |= 1;  // R/mixdir_vi.R:105-108
-    if (diff < a.epsilon) conv = 1;    // R/mixdir_vi.R:109
-  }
-  a.trace[it] = elbo;
-  s->elbo = elbo;
-  s->converged = conv;
-  s->warn = warn;
-  s->underflow = (*a.underflow > 0.0) ? 1 : 0;
-  s->bad = (*a.bad > 0.0) ? 1 : 0;
-  s->iter = it;
-}
 
 // ---------------------------------------------------------------------------
 // results: U = phi / sum(phi) (R/mixdir_vi.R:119-130), final omega/kappa and
@@ -536,44 +293,6 @@ __global__ void k_table_to_ragged(ScatterRagArgs a, double* out) {
 // statistics buffer:  [ S : NR*KP | cs : KP | H | underflow | nNA | bad ]   (doubles)
 // ---------------------------------------------------------------------------
 
-// deterministic reduction of the per-cluster partials of the fused kernel
-struct ReduceArgs {
-  int NR, KP;
-  int n_clusters, n_ctas;
-  const double* Spart;   // [n_clusters][NR*KP]
-  const double* cspart;  // [n_clusters][KP]
-  const double* Hpart;   // [n_ctas]
-  const int* underflow;  // device flag
-  const ScanOut* scan;   // NA count / validity of this rank's codes
-  const uint8_t* na_row; // [NR] 1 for NA rows (their S entries are scratch)
-  double* stats;
-};
-__global__ void k_reduce_partials(ReduceArgs a) {
-  const size_t n = (size_t)a.NR * a.KP;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
-       e += (size_t)gridDim.x * blockDim.x) {
-    double s = 0;
-    if (!a.na_row[e / a.KP])
-      for (int c = 0; c < a.n_clusters; c++) s += a.Spart[(size_t)c * n + e];
-    a.stats[e] = s;
-  }
-  if (blockIdx.x == 0) {
-    for (int k = threadIdx.x; k < a.KP; k += blockDim.x) {
-      double s = 0;
-      for (int c = 0; c < a.n_clusters; c++) s += a.cspart[(size_t)c * a.KP + k];
-      a.stats[n + k] = s;
-    }
-    if (threadIdx.x == 0) {
-      double h = 0;
-      for (int c = 0; c < a.n_ctas; c++) h += a.Hpart[c];
-      a.stats[n + a.KP] = h;
-      a.stats[n + a.KP + 1] = (*a.underflow) ? 1.0 : 0.0;
-      a.stats[n + a.KP + 2] = (double)a.scan->n_missing;
-      a.stats[n + a.KP + 3] = a.scan->bad ? 1.0 : 0.0;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Units: what the fused kernels gather and scatter is a UNIT -- one feature, or a PAIR of
 // features (ja, jb) whose codes are combined at upload into one byte
@@ -631,7 +350,15 @@ __global__ void k_pack_units(const uint8_t* __restrict__ raw, int row_bytes, int
 }
 static_assert(sizeof(UnitDesc) == 16, "UnitDesc is read as int4");
 
-// unit table from the feature table: T2[g2][k] = T[src.x][k] + T[src.y][k]  (src.y < 0: single)
+// feature-table row g = (j, x) collects the unit rows start + i*stride, i < count
+// (count 0: NA row, its statistics are never used)
+struct MargDesc {
+  int start, stride, count, pad;
+};
+
+// unit table from the feature table: T2[g2][k] = T[src.x][k] + T[src.y][k]  (src.y < 0: single).
+// Only the unit-test door (mixdir_b200_estep) needs it as a kernel of its own; inside a fit the
+// iteration kernel (iter.cuh) builds T2 element by element.
 __global__ void k_build_T2(const int2* __restrict__ src, int NR2, int KP, const double* __restrict__ T,
                            double* __restrict__ T2) {
   const size_t n = (size_t)NR2 * KP;
@@ -645,14 +372,12 @@ __global__ void k_build_T2(const int2* __restrict__ src, int NR2, int KP, const 
   }
 }
 
-// feature-table row g = (j, x) collects the unit rows start + i*stride, i < count
-// (count 0: NA row, its statistics are never used)
-struct MargDesc {
-  int start, stride, count, pad;
-};
-
 // deterministic reduction of the per-cluster partials over clusters AND over the partner
-// feature's codes: unit statistics S2 -> feature statistics S
+// feature's codes: unit statistics S2 -> feature statistics S.
+// One block per (feature-table row, 32 classes); the count * n_clusters terms of a row are dealt
+// round-robin to the 8 warps (lanes = classes: 256-byte coalesced reads), every warp adds its
+// terms in index order and warp 0 adds the 8 partial sums in warp order: a fixed summation tree,
+// ~150 dependent loads per thread at S4 instead of the 1184 a thread-per-output loop needs.
 struct ReduceUnitsArgs {
   int NR, NR2, KP;
   int n_clusters, n_ctas;
@@ -663,29 +388,38 @@ struct ReduceUnitsArgs {
   const ScanOut* scan;
   const MargDesc* marg;  // [NR]
   double* stats;
+  const int* stop;       // fit already over (converged / error): nothing to do
 };
-__global__ void k_reduce_units(ReduceUnitsArgs a) {
+__global__ void __launch_bounds__(256) k_reduce_units(ReduceUnitsArgs a) {
+  __shared__ double part[8][32];
+  if (a.stop && *a.stop) return;
   const size_t n = (size_t)a.NR * a.KP;
   const size_t n2 = (size_t)a.NR2 * a.KP;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
-       e += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(e / a.KP), k = (int)(e - (size_t)g * a.KP);
-    const int4 mm = __ldg(reinterpret_cast<const int4*>(a.marg) + g);
-    const MargDesc m = {mm.x, mm.y, mm.z, mm.w};
-    double s = 0;
-    for (int i = 0; i < m.count; i++) {
-      const size_t e2 = (size_t)(m.start + i * m.stride) * a.KP + k;
-      double t = 0;
-      for (int c = 0; c < a.n_clusters; c++) t += a.Spart[(size_t)c * n2 + e2];
-      s += t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x, k = blockIdx.y * 32 + lane;
+  const int4 mm = __ldg(reinterpret_cast<const int4*>(a.marg) + g);
+  const MargDesc m = {mm.x, mm.y, mm.z, mm.w};
+  const int terms = m.count * a.n_clusters;
+  double s = 0;
+  if (k < a.KP) {
+    for (int t = warp; t < terms; t += 8) {
+      const int i = t / a.n_clusters, c = t - i * a.n_clusters;
+      s += a.Spart[(size_t)c * n2 + (size_t)(m.start + i * m.stride) * a.KP + k];
     }
-    a.stats[e] = s;
   }
-  if (blockIdx.x == 0) {
-    for (int k = threadIdx.x; k < a.KP; k += blockDim.x) {
-      double s = 0;
-      for (int c = 0; c < a.n_clusters; c++) s += a.cspart[(size_t)c * a.KP + k];
-      a.stats[n + k] = s;
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && k < a.KP) {
+    double t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; w++) t += part[w][lane];
+    a.stats[(size_t)g * a.KP + k] = t;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int kk = threadIdx.x; kk < a.KP; kk += blockDim.x) {
+      double t = 0;
+      for (int c = 0; c < a.n_clusters; c++) t += a.cspart[(size_t)c * a.KP + kk];
+      a.stats[n + kk] = t;
     }
     if (threadIdx.x == 0) {
       double h = 0;
@@ -699,7 +433,8 @@ __global__ void k_reduce_units(ReduceUnitsArgs a) {
 }
 
 // tail of the statistics buffer for the generic kernel: [underflow | nNA | bad]
-__global__ void k_tail_to_stats(const int* underflow, const ScanOut* scan, double* slot) {
+__global__ void k_tail_to_stats(const int* underflow, const ScanOut* scan, double* slot, const int* stop) {
+  if (*stop) return;
   slot[0] = (*underflow) ? 1.0 : 0.0;
   slot[1] = (double)scan->n_missing;
   slot[2] = scan->bad ? 1.0 : 0.0;
@@ -727,6 +462,7 @@ struct GenericArgs {
   int64_t zeta_row0;       // row offset of this launch inside zeta_out
   int do_scatter;
   const int* bad;          // invalid codes seen by the upload scan: do nothing
+  const int* stop;         // fit already over (converged / error): do nothing
 };
 
 template <int CB>
@@ -736,7 +472,7 @@ __global__ void __launch_bounds__(256) k_em_generic(GenericArgs a) {
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int K = a.K, KP = a.KP;
   const int cpl = (K + 31) >> 5;
-  if (*a.bad) return;  // a code above C_j would index outside the tables
+  if (*a.bad || *a.stop) return;  // a code above C_j would index outside the tables
   double csacc[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) csacc[c] = 0;

@@ -59,6 +59,7 @@ struct UnitArgs {
   int* underflow;
   int accumulate;
   const int* bad;
+  const int* stop;         // fit already over (converged / error): do nothing
 };
 
 struct UnitSmem {
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
   const uint32_t tile_bytes = (uint32_t)R * WPR * 4;
-  if (*a.bad) return;  // uniform over the grid: a code above C_j would index outside the tables
+  // uniform over the grid: a code above C_j would index outside the tables / the fit is over
+  if (*a.bad || *a.stop) return;
 
   // ---- prologue: barriers, first tile in flight, tables into shared memory ----
   if (threadIdx.x == 0) {

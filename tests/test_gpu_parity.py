@@ -13,6 +13,9 @@ pytestmark = pytest.mark.gpu
 CP_ATOL = 1e-6    # class_prob, absolute   (north_star)
 ELBO_RTOL = 1e-9  # ELBO, relative         (north_star)
 
+ENGINES = [1, 2, 4]  # generic (global tables + atomics), fused (row-major codes), units (default)
+ENGINE_IDS = ["generic", "fused", "units"]
+
 FIT_FIXTURES = [
     "fit_toy_k3.npz", "fit_toy_dp_k10.npz", "fit_toy_na_k3.npz", "fit_toy_na_dp_k10.npz",
     "fit_m1_seed1.npz", "fit_m1_seed2.npz", "fit_m1_seed3.npz", "fit_m1_seed4.npz",
@@ -33,7 +36,7 @@ def rel(a, b):
     return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300))
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3, 4], ids=["generic", "fused", "bucket", "units"])
+@pytest.mark.parametrize("engine", ENGINES, ids=ENGINE_IDS)
 @pytest.mark.parametrize("name", FIT_FIXTURES)
 def test_fit_matches_golden(name, engine, mushroom):
     g = load_golden(name)
@@ -68,7 +71,7 @@ def test_fit_matches_golden(name, engine, mushroom):
     assert r["warn_flags"] == int(g["warn_flags"])
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3, 4], ids=["generic", "fused", "bucket", "units"])
+@pytest.mark.parametrize("engine", ENGINES, ids=ENGINE_IDS)
 @pytest.mark.parametrize("tag", ["k3", "k10"])
 def test_estep_matches_reference_native_functions(tag, engine):
     """kernel zeta / statistics vs the reference's own update_zeta_cpp / update_zeta_dp_cpp /
@@ -119,7 +122,7 @@ def test_fit_live_oracle_random_shapes():
         z0 = synth.zeta_init(case, N, K)
         p0 = synth.phi_init(case, ncat, K)
         ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, dp, 1.0, 1.0, 0.1, 25, 1e-3, z0, p0)
-        for engine in (1, 2, 3, 4):
+        for engine in ENGINES:
             with Engine(codes, ncat) as eng:
                 eng.set_engine(engine)
                 r = eng.fit(K, z0.sum(axis=0), p0, dp=bool(dp), max_iter=25, epsilon=1e-3,
@@ -173,7 +176,7 @@ def test_underflow_is_an_error(dp):
     codes2, _ = synth.make_codes(1, 64, ncat2, 2)
     p_big = synth.phi_init(1, ncat2, 2).copy()
     p_big[::2] = 1e-300  # psi(1e-300) ~ -1e300: every logit underflows
-    for engine in (2, 3, 4):
+    for engine in (2, 4):
         with Engine(codes2, ncat2) as eng:
             eng.set_engine(engine)
             with pytest.raises(ZetaUnderflow):
@@ -190,7 +193,7 @@ def test_create_from_r_matrix_and_u16():
     ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, 0, 1.0, 1.0, 0.1, 10, 1e-3, z0, p0)
     for make in (lambda: Engine(codes, ncat),
                  lambda: Engine.from_r_matrix(po.codes_to_r_matrix(codes), ncat)):
-        for engine in (1, 2, 3):
+        for engine in (1, 2):
             with make() as eng:
                 assert eng.n_missing == int((codes == 0).sum())
                 assert eng.max_code == int(codes.max())
@@ -233,19 +236,15 @@ def test_full_size_properties():
     p0 = synth.phi_init(2, pat, K)
     cs0 = np.full(K, N / K)
     outs = {}
-    for engine in (1, 2, 3, 4):
+    for engine in ENGINES:
         with Engine(codes, pat) as eng:
             eng.set_engine(engine)
             outs[engine] = eng.fit(K, cs0, p0, max_iter=4, epsilon=-np.inf, want_class_prob=False)
             outs[engine]["timing"] = eng.timing()
-    assert outs[3]["timing"]["engine"] == 3
     assert outs[4]["timing"]["engine"] == 4 and outs[4]["timing"]["unit_pairs"] > 0
     assert rel(outs[4]["convergence"], outs[2]["convergence"]) < 1e-11
     assert np.array_equal(outs[4]["pred_class"], outs[2]["pred_class"])
     np.testing.assert_allclose(outs[4]["phi"], outs[2]["phi"], rtol=1e-9, atol=1e-9)
-    assert rel(outs[3]["convergence"], outs[2]["convergence"]) < 1e-11
-    assert np.array_equal(outs[3]["pred_class"], outs[2]["pred_class"])
-    np.testing.assert_allclose(outs[3]["phi"], outs[2]["phi"], rtol=1e-9, atol=1e-9)
     a, b = outs[1], outs[2]
     assert rel(a["convergence"], b["convergence"]) < 1e-11
     np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-9, atol=1e-9)
@@ -309,7 +308,7 @@ def test_recycled_buffers_do_not_leak_stale_codes():
     z0 = synth.zeta_init(3, n, 3)
     p0 = synth.phi_init(3, ncat, 3)
     ref = po.fit(po.codes_to_r_matrix(codes), ncat, 3, 0, 1.0, 1.0, 0.1, 6, -np.inf, z0, p0)
-    for engine in (2, 3, 1, 4):
+    for engine in (2, 1, 4):
         with Engine(codes, ncat) as eng:
             eng.set_engine(engine)
             r = eng.fit(3, z0.sum(axis=0), p0, max_iter=6, epsilon=-np.inf)
@@ -350,7 +349,7 @@ def test_feature_pair_units_against_oracle(K, J, p_na):
         assert pairs[(2, True)] > 0 and pairs[(4, True)] > 0, pairs
 
 
-@pytest.mark.parametrize("engine", [2, 3, 4])
+@pytest.mark.parametrize("engine", [2, 4])
 def test_chunked_first_iteration_equals_resident_fit(engine):
     """With n_cat_bound given, fit() starts while the upload is still in flight: the first pass runs
     chunk by chunk (scan -> pack unit codes -> E+M on the rows that have landed, partial statistics
