@@ -359,7 +359,7 @@ def run_ours(args):
                                  tm["engine"] == traffic.get("engine", 2) and J == 60 and K == 32
                                  else None),
                      "traffic_source": (traffic or {}).get("source"),
-                     "kernel": {2: "k_em_fused", 3: "k_em_bucket", 4: "k_em_units"}.get(tm["engine"],
+                     "kernel": {2: "k_em_fused", 4: "k_em_units", 5: "k_em_seg"}.get(tm["engine"],
                                                                                        "k_em_generic"),
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,

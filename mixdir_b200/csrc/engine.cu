@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "units.cuh"
+#include "seg.cuh"
 #include "iter.cuh"
 #include "predict.cuh"
 #include "features.cuh"
@@ -151,8 +152,21 @@ struct UnitPlan {
   std::vector<int> eoff_rot;   // [4][U] byte offsets, rotated (units.cuh)
 };
 
+// engine 5 (k_em_seg): layout of a tile's segment lists (seg.cuh)
+struct SegPlan {
+  bool fs = false;  // feature split: the two CTAs of a cluster own half of the features each
+  int G = 0;        // group padding, entries
+  int TB = 0;       // bytes per tile
+  // per M-step owner (fs: 2, else 1): block inside a tile's lists, jobs, statistics rows
+  int blk_off[2] = {0, 0}, blk_size[2] = {0, 0};
+  int job0[2] = {0, 0}, njobs[2] = {0, 0};
+  int sc0[2] = {0, 0}, SC[2] = {0, 0};
+  std::vector<int4> jobs;         // {idx_off, cnt_off (inside the owner's block), C_j | feature << 8, first statistics row}
+  std::vector<int> srow_to_stat;  // shared-memory statistics row -> feature-table row, owner after owner
+};
+
 struct Plan {
-  int engine = 0;  // 1 generic, 2 fused, 4 units
+  int engine = 0;  // 1 generic, 2 fused, 4 units, 5 sorted segments
   int KP = 0;
   int KC = 0, P = 1, RG = 8, W = 0;
   int FPG = 4;  // engine 4: elements per M-step rotation group
@@ -160,6 +174,7 @@ struct Plan {
   size_t smem = 0;
   int R = 0;  // rows per tile
   UnitPlan up;
+  SegPlan sp;
 };
 
 struct Shard {
@@ -199,6 +214,10 @@ struct Shard {
   int* d_eoff = nullptr;           // engine 4: rotated element offsets
   uint8_t* d_ucodes = nullptr;     // [n_rows + kRowPad][WPRu] words (null: identity plan)
   int64_t packed_rows = 0;         // rows of d_ucodes already packed
+  unsigned char* d_seg = nullptr;  // engine 5: [n_tiles][TB] segment lists
+  int4* d_jobs = nullptr;
+  int* d_srow2stat = nullptr;
+  int64_t seg_tiles = 0;           // tiles of d_seg already built
   double* d_T2 = nullptr;          // [NR2][KP] (workspace)
   int ws_NR2 = 0;
   PriorState* d_prior = nullptr;
@@ -260,6 +279,9 @@ static int allreduce(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t cou
   NCCL_TRY(nccl::GroupEnd());
   return MIXDIR_B200_OK;
 }
+
+struct Plan;
+static int allreduce_stats(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t tab, const Plan& pl);
 
 // ---------------------------------------------------------------------------
 // block cache: device and page-locked allocations are recycled across handles (cudaMalloc,
@@ -405,6 +427,7 @@ static void free_shard(Shard& s) {
   dfree(s.d_na_feat);
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
   dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
+  dfree(s.d_seg); dfree(s.d_jobs); dfree(s.d_srow2stat);
   s.unit_valid = false;
   if (s.copy_stream) {
     cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
@@ -879,6 +902,7 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 // ---------------------------------------------------------------------------
 typedef void (*fused_fn)(FusedArgs);
 typedef void (*units_fn)(UnitArgs);
+typedef void (*seg_fn)(SegArgs);
 static void layout_units(UnitPlan* up, int KC);
 
 static fused_fn pick_fused(int KC, int CB, int RG) {
@@ -894,7 +918,14 @@ static fused_fn pick_fused(int KC, int CB, int RG) {
 }
 
 static units_fn pick_units(int KC, int RG, int FPG, int W);
+static seg_fn pick_seg(int KC, int W, bool fs) {
+  if (KC == 16 && fs) return k_em_seg<16, 512, true>;
+  if (KC == 16) return k_em_seg<16, 512, false>;
+  if (KC == 32) return W > 16 ? k_em_seg<32, 640, false> : k_em_seg<32, 512, false>;
+  return nullptr;
+}
 static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
+  if (p.engine == 5) return (const void*)pick_seg(p.KC, p.W, p.sp.fs);
   if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG, p.W);
   return (const void*)pick_fused(p.KC, h->CB, p.RG);
 }
@@ -1198,6 +1229,131 @@ static bool plan_units(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) 
   return true;
 }
 
+// the per-iteration exchange step: sum the statistics buffer over shards / ranks.  Engine 5 keeps
+// S as int64 fixed point (exact, order-independent sums) and the tail [cs | H | underflow | nNA |
+// bad] as doubles.
+static int allreduce_stats(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t tab, const Plan& pl) {
+  if (!needs_allreduce(h)) return MIXDIR_B200_OK;
+  if (pl.engine != 5) return allreduce(h, bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum);
+  RET_IF(allreduce(h, bufs, tab, nccl::kInt64, nccl::kSum));
+  std::vector<void*> tails(bufs.size());
+  for (size_t i = 0; i < bufs.size(); i++) tails[i] = (double*)bufs[i] + tab;
+  return allreduce(h, tails, pl.KP + 4, nccl::kDouble, nccl::kSum);
+}
+
+// engine 5: layout of the segment lists of a tile of R rows (seg.cuh).  fs: the features are dealt
+// alternately to the two CTAs of a cluster (the C_j pattern of neighbouring features balances).
+static void layout_seg(const mixdir_b200_handle* h, int R, int G, bool fs, int W, SegPlan* sp) {
+  const int J = h->J;
+  *sp = SegPlan();
+  sp->fs = fs;
+  sp->G = G;
+  const int owners = fs ? 2 : 1;
+  int blk = 0;
+  for (int o = 0; o < owners; o++) {
+    std::vector<int> feats;
+    for (int j = 0; j < J; j++)
+      if (!fs || j % 2 == o) feats.push_back(j);
+    // warp w works on jobs w, w + W, ...: order them by falling C_j (more categories = more groups
+    // = more per-group work) and deal the rounds in snake order so the warps finish together
+    std::stable_sort(feats.begin(), feats.end(), [&](int a, int b) { return h->ncat[a] > h->ncat[b]; });
+    for (size_t r0 = (size_t)W; r0 < feats.size(); r0 += 2 * (size_t)W)
+      std::reverse(feats.begin() + r0, feats.begin() + std::min(feats.size(), r0 + W));
+    sp->job0[o] = (int)sp->jobs.size();
+    sp->njobs[o] = (int)feats.size();
+    sp->sc0[o] = (int)sp->srow_to_stat.size();
+    int cnt_bytes = 0, sc = 0;  // a job's group counts start at a 4-byte boundary
+    for (int j : feats) {
+      cnt_bytes += (h->ncat[j] + 3) & ~3;
+      sc += h->ncat[j];
+    }
+    sp->SC[o] = sc;
+    int off = (cnt_bytes + 15) & ~15, c0 = 0, s0 = 0;
+    for (int j : feats) {
+      sp->jobs.push_back(make_int4(off, c0, h->ncat[j] | (j << 8), s0));
+      for (int c = 1; c <= h->ncat[j]; c++) sp->srow_to_stat.push_back(h->rowoff[j] + c);
+      c0 += (h->ncat[j] + 3) & ~3;
+      s0 += h->ncat[j];
+      off += (R + (G - 1) * std::min(h->ncat[j], R) + 15) & ~15;
+    }
+    sp->blk_off[o] = blk;
+    sp->blk_size[o] = off;
+    blk += off;
+  }
+  sp->TB = blk;
+}
+
+// engine 5: k_em_seg.  Classes per CTA 16 or 32, 8 row groups per lane, tiles of at most 255 rows
+// (row numbers are bytes, 255 is the dummy).  MIXDIR_B200_FORCE_PLAN="KC,-,pairs,-,W" restricts
+// the search as for the unit kernel.
+static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
+  if (h->CB != 1) return false;
+  int fKC = -1, fRG = -1, fM = -1, fFPG = -1, fW = -1;
+  if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN"))
+    sscanf(f, "%d,%d,%d,%d,%d", &fKC, &fRG, &fM, &fFPG, &fW);
+  const uint8_t* na = (h->scan_resolved && (int)h->has_na.size() == h->J && !getenv("MIXDIR_B200_KEEP_NA_ROWS"))
+                          ? h->has_na.data() : nullptr;
+  Plan best;
+  double best_cost = 1e300;
+  const int kcs[2] = {32, 16};
+  for (int KC : kcs) {
+    if (fKC > 0 && KC != fKC) continue;
+    if (KC == 32 && K <= 16) continue;
+    const int RPW = 32 / KC, RG = 8;
+    const int P = (K + KC - 1) / KC;
+    if (P > 8) continue;
+    const int Wmax = fW > 0 ? fW : (KC == 16 ? 15 : 20);
+    for (int W = Wmax; W >= 4; W--) {
+      if (fW > 0 && W != fW) continue;
+      const int R = W * RG * RPW;
+      if (R > kSegDummyRow) continue;
+      Plan c;
+      const bool fs = KC == 16 && P == 2 && !getenv("MIXDIR_B200_NO_FEATURE_SPLIT");
+      layout_seg(h, R, fs ? 4 : 4 * RPW, fs, W, &c.sp);
+      const int maxSC = std::max(c.sp.SC[0], c.sp.SC[1]), maxJobs = std::max(c.sp.njobs[0], c.sp.njobs[1]);
+      const int maxBlk = std::max(c.sp.blk_size[0], c.sp.blk_size[1]);
+      UnitPlan up;
+      bool found = false;
+      const int m_hi = fM >= 0 ? std::min(fM, h->J / 2) : (h->pairing ? h->J / 2 : 0);
+      const int w_lo = (h->J - m_hi + 3) / 4, w_hi = (h->J + 3) / 4;
+      for (int w = w_lo; w <= w_hi; w++) {
+        const int m = fM >= 0 ? m_hi : std::max(0, h->J - 4 * w);
+        if (m > m_hi || !make_units(h, m, &up, true, na)) continue;
+        layout_units(&up, KC);
+        if (((size_t)R * up.WPRu) % 4 != 0) continue;  // a tile is one bulk copy: 16-byte multiple
+        const size_t tot = SegSmem(up.srows, maxSC, fs ? 32 : KC, KC, W, RG, up.WPRu, maxJobs, maxBlk).total;
+        if (tot > (size_t)s.smem_optin) continue;
+        c.smem = tot;
+        found = true;
+        break;
+      }
+      if (!found) continue;
+      c.engine = 5; c.KC = KC; c.P = P; c.RG = RG; c.W = W; c.KP = P * KC; c.R = R; c.FPG = 0;
+      c.up = up;
+      c.n_clusters = plan_occupancy(h, s, c);
+      if (c.n_clusters < 1) continue;
+      // shared-memory cycles per row and CTA: one 128-byte wavefront per (row, element) and 16
+      // classes in the E-step; the M-step reads 4 bytes per (row, feature, class) but is bound by
+      // instruction issue (~0.8 cycles per row and feature at KC=16, ~1.5 at KC=32); warps idle in
+      // the last round of the feature rotation; per-row overhead (soft-max, exchange) as in plan_units
+      const double used = std::min(1.0, (double)c.n_clusters * P / s.sm_count);
+      const int rounds = (maxJobs + W - 1) / W;
+      const double e_cost = up.U * (KC / 16.0);
+      const double m_cost = (fs ? 1.5 : (KC == 16 ? 1.6 : 1.5)) * rounds * W;
+      const double ovh = KC == 16 ? 65.0 : 80.0;
+      const double wpen = W >= 15 ? 1.0 : (W >= 12 ? 1.05 : (W >= 8 ? 1.2 : 1.5));
+      const double cost = P * (e_cost + m_cost + ovh) * wpen / used + P * 3000.0 / R;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = c;
+      }
+    }
+  }
+  if (best.engine != 5) return false;
+  *out = best;
+  return true;
+}
+
 // host-only view of the unit kernel's shared-memory placement for KC classes per CTA (CPU tests)
 extern "C" int mixdir_b200_unit_layout(int n_features, const int* ncat, int n_pairs,
                                        const unsigned char* has_na, int classes_per_cta,
@@ -1280,11 +1436,19 @@ static bool plan_fused(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) 
   return true;
 }
 
-// engine_pref: 0 automatic (unit kernel, else fused, else generic), 1 generic, 2 fused, 4 units.
+// engine_pref: 0 automatic (segment kernel, else unit kernel, else fused, else generic), 1 generic,
+// 2 fused, 4 units, 5 sorted segments.
 // Planning happens on the first shard's device (all shards of a handle are the same GPU model).
 static int plan_engine(mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   CU_TRY(cudaSetDevice(s.device));
   const int pref = h->engine_pref;
+  // Automatic mode takes the segment kernel from 16384 rows on: below, rounding the responsibilities
+  // to 2^-31 can cost more than 1e-9 of the ELBO (seg.cuh), and such fits are launch-bound anyway.
+  const bool seg_ok = pref == 5 || h->n_rows * (int64_t)h->world >= 16384;
+  if ((pref == 0 || pref == 5) && seg_ok && plan_seg(h, s, K, out)) return MIXDIR_B200_OK;
+  if (pref == 5)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "segment kernel does not fit this problem shape (K, sum C_j) "
+                                          "or the codes are 2 bytes wide");
   if ((pref == 0 || pref == 4) && plan_units(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 4)
     return fail(MIXDIR_B200_BAD_ARGUMENT, "unit kernel does not fit this problem shape (K, sum C_j) "
@@ -1306,7 +1470,7 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   const int nclus = pl.engine >= 2 ? pl.n_clusters : 0;
   const int nctas = nclus * pl.P;
   if (s.ws_K == K && s.ws_KP == KP && s.ws_iter >= max_iter && s.ws_clusters >= nclus &&
-      s.ws_ctas >= nctas && s.ws_NR2 >= pl.up.NR2)
+      s.ws_ctas >= nctas && s.ws_NR2 >= pl.up.NR2 && (pl.engine == 5 || nclus == 0 || s.d_Spart))
     return MIXDIR_B200_OK;
   free_workspace(s);
   const size_t tab = (size_t)h->NR * KP;
@@ -1331,7 +1495,7 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   RET_IF(dalloc(&s.d_prior, 1));
   RET_IF(dalloc(&s.d_status, 1));
   if (nclus > 0) {
-    RET_IF(dalloc(&s.d_Spart, (size_t)nclus * tab2));
+    if (pl.engine != 5) RET_IF(dalloc(&s.d_Spart, (size_t)nclus * tab2));
     RET_IF(dalloc(&s.d_cspart, (size_t)nclus * KP));
     RET_IF(dalloc(&s.d_Hpart, nctas));
   }
@@ -1401,6 +1565,9 @@ static size_t unit_stage_bytes(const UnitPlan& up) {
          pad8(up.slot.size() * sizeof(int)) + pad8(up.eoff_rot.size() * sizeof(int)) +
          2 * pad8(up.desc.size() * sizeof(int2)) + 10 * 64;
 }
+static size_t seg_stage_bytes(const SegPlan& sp) {
+  return pad8(sp.jobs.size() * sizeof(int4)) + pad8(sp.srow_to_stat.size() * sizeof(int)) + 2 * 64;
+}
 
 template <typename T>
 static int send_vec(Shard& s, T** dptr, const std::vector<T>& vec) {
@@ -1419,13 +1586,16 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
   std::vector<UnitDesc> sig = up.desc;  // element order + what the placement depends on
   sig.push_back(UnitDesc{pl.engine, pl.KC, up.Q, up.srows});
   sig.push_back(UnitDesc{pl.R, pl.RG, pl.W, pl.FPG});
+  sig.push_back(UnitDesc{pl.sp.fs ? 1 : 0, pl.sp.G, pl.sp.TB, 0});
   if (s.unit_valid && s.unit_sig.size() == sig.size() &&
       memcmp(s.unit_sig.data(), sig.data(), sig.size() * sizeof(UnitDesc)) == 0)
     return MIXDIR_B200_OK;
   s.unit_valid = false;
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
   dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
+  dfree(s.d_seg); dfree(s.d_jobs); dfree(s.d_srow2stat);
   s.packed_rows = 0;
+  s.seg_tiles = 0;
   {  // k_iter's work list: the real elements (feature, or the two features of a pair)
     std::vector<int2> elem, erange;
     for (int e = 0; e < up.U; e++) {
@@ -1451,14 +1621,20 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
     const size_t rowb = (size_t)up.WPRu * 4;
     // engine 4 stores the packed codes tile by tile ([tile][word][row in tile]): whole tiles,
     // the tail of the last one zeroed; engine 2 row-major with kRowPad zero rows behind
-    const int64_t R = pl.engine == 4 ? pl.R : 1;
+    const int64_t R = pl.engine >= 4 ? pl.R : 1;
     const int64_t full = s.n_rows / R * R, rows_alloc = (s.n_rows + R - 1) / R * R + kRowPad;
     RET_IF(dalloc(&s.d_ucodes, (size_t)rows_alloc * rowb));
     CU_TRY(cudaMemsetAsync(s.d_ucodes + (size_t)full * rowb, 0, (size_t)(rows_alloc - full) * rowb, s.stream));
   }
-  if (pl.engine == 4) {
+  if (pl.engine >= 4) {
     RET_IF(send_vec(s, &s.d_slot, up.slot));
     RET_IF(send_vec(s, &s.d_eoff, up.eoff_rot));
+  }
+  if (pl.engine == 5) {
+    RET_IF(send_vec(s, &s.d_jobs, pl.sp.jobs));
+    RET_IF(send_vec(s, &s.d_srow2stat, pl.sp.srow_to_stat));
+    const int64_t n_tiles = (s.n_rows + pl.R - 1) / pl.R;
+    RET_IF(dalloc(&s.d_seg, (size_t)std::max<int64_t>(n_tiles, 1) * pl.sp.TB));
   }
   s.unit_sig = sig;
   s.unit_valid = true;
@@ -1472,7 +1648,7 @@ static int pack_units(mixdir_b200_handle* h, Shard& s, const Plan& pl, int64_t u
   const int WPRu = pl.up.WPRu;
   const int grid = (int)std::min<int64_t>((int64_t)s.sm_count * 16, (nr * WPRu + 255) / 256);
   k_pack_units<<<grid, 256, 0, s.stream>>>(s.d_codes + (size_t)r0 * h->row_bytes, h->row_bytes, nr,
-                                           s.d_udesc, WPRu, pl.engine == 4 ? pl.R : 0,
+                                           s.d_udesc, WPRu, pl.engine >= 4 ? pl.R : 0,
                                            reinterpret_cast<uint32_t*>(s.d_ucodes) + (size_t)r0 * WPRu);
   CU_TRY(cudaGetLastError());
   s.packed_rows = upto;
@@ -1480,7 +1656,32 @@ static int pack_units(mixdir_b200_handle* h, Shard& s, const Plan& pl, int64_t u
   return MIXDIR_B200_OK;
 }
 
-// unit table T2 from the feature table T (after every k_param)
+// engine 5: build the segment lists of the tiles that end at or before row `upto` (or hold the
+// last rows of the shard); their raw codes must have been consumed from the upload
+static int pack_seg(mixdir_b200_handle* h, Shard& s, const Plan& pl, int64_t upto, int* launches) {
+  if (pl.engine != 5) return MIXDIR_B200_OK;
+  const int64_t t1 = upto >= s.n_rows ? (s.n_rows + pl.R - 1) / pl.R : upto / pl.R;
+  if (t1 <= s.seg_tiles) return MIXDIR_B200_OK;
+  const int64_t t0 = s.seg_tiles;
+  PackSegArgs a;
+  a.raw = s.d_codes + (size_t)t0 * pl.R * h->row_bytes;
+  a.row_bytes = h->row_bytes;
+  a.n_rows = s.n_rows - t0 * pl.R;
+  a.n_tiles = (int)(t1 - t0);
+  a.R = pl.R; a.J = h->J; a.G = pl.sp.G; a.TB = pl.sp.TB;
+  a.split = pl.sp.njobs[0];
+  a.blk_off[0] = pl.sp.blk_off[0]; a.blk_off[1] = pl.sp.blk_off[1];
+  a.jobs = s.d_jobs;
+  a.out = s.d_seg + (size_t)t0 * pl.sp.TB;
+  const int grid = (int)std::min<int64_t>(a.n_tiles, (int64_t)s.sm_count * 32);
+  k_pack_seg<<<grid, 256, 0, s.stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  s.seg_tiles = t1;
+  if (launches) *launches += 1;
+  return MIXDIR_B200_OK;
+}
+
+// unit table T2 from the feature table T (unit-test door; a fit builds it in k_iter)
 static int build_unit_table(Shard& s, const Plan& pl) {
   if (pl.up.identity) return MIXDIR_B200_OK;
   const size_t n = (size_t)pl.up.NR2 * pl.KP;
@@ -1527,7 +1728,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
 
   if (pl.engine >= 2 && s.n_rows > 0) {
     if (chunked) {  // partial buffers accumulate over the launches
-      CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab2 * sizeof(double), s.stream));
+      if (pl.engine != 5)
+        CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab2 * sizeof(double), s.stream));
       CU_TRY(cudaMemsetAsync(s.d_cspart, 0, (size_t)pl.n_clusters * pl.KP * sizeof(double), s.stream));
       CU_TRY(cudaMemsetAsync(s.d_Hpart, 0, (size_t)pl.n_clusters * pl.P * sizeof(double), s.stream));
     }
@@ -1538,6 +1740,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       const int64_t r0 = ranges[i].first, nr = ranges[i].second - ranges[i].first;
       if (nr <= 0) continue;
       RET_IF(pack_units(h, s, pl, ranges[i].second, launches));
+      RET_IF(pack_seg(h, s, pl, ranges[i].second, launches));
       const int n_tiles = (int)((nr + pl.R - 1) / pl.R);
       const int nclus = std::min(pl.n_clusters, n_tiles);
       max_clus = std::max(max_clus, nclus);
@@ -1573,7 +1776,46 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      if (pl.engine == 4) {
+      if (pl.engine == 5) {
+        SegArgs g;
+        g.codes = a.codes;
+        g.seg = s.d_seg + (size_t)(r0 / pl.R) * pl.sp.TB;
+        g.n_rows = nr;
+        g.n_tiles = n_tiles;
+        g.WPR = up.WPRu;
+        g.NR2 = up.NR2;
+        g.srows = up.srows;
+        g.K = K;
+        g.KP = pl.KP;
+        g.P = pl.P;
+        g.TB = pl.sp.TB;
+        for (int o = 0; o < 2; o++) {
+          g.blk_off[o] = pl.sp.blk_off[o]; g.blk_size[o] = pl.sp.blk_size[o];
+          g.job0[o] = pl.sp.job0[o]; g.njobs[o] = pl.sp.njobs[o];
+          g.sc0[o] = pl.sp.sc0[o]; g.SC[o] = pl.sp.SC[o];
+        }
+        g.maxSC = std::max(pl.sp.SC[0], pl.sp.SC[1]);
+        g.maxJobs = std::max(pl.sp.njobs[0], pl.sp.njobs[1]);
+        g.maxBlk = std::max(pl.sp.blk_size[0], pl.sp.blk_size[1]);
+        g.eoff_rot = s.d_eoff;
+        g.slot_of_row = s.d_slot;
+        g.T2 = s.d_T2;
+        g.logprior = s.d_logprior;
+        g.jobs = s.d_jobs;
+        g.srow_to_stat = s.d_srow2stat;
+        g.stats = reinterpret_cast<unsigned long long*>(s.d_stats);
+        g.stats_tail = s.d_stats + tab;
+        g.Hpart = s.d_Hpart;
+        g.cspart = s.d_cspart;
+        g.n_hsum = (chunked ? pl.n_clusters : nclus) * pl.P;
+        g.ticket = s.d_ticket;
+        g.underflow = s.d_underflow;
+        g.scan = s.d_scan;
+        g.accumulate = chunked ? 1 : 0;
+        g.bad = &s.d_scan->bad;
+        g.stop = stop;
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_seg(pl.KC, pl.W, pl.sp.fs), g));
+      } else if (pl.engine == 4) {
         UnitArgs u;
         u.codes = a.codes;
         u.n_rows = nr;
@@ -1602,6 +1844,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       *launches += 1;
     }
     if (ev1) CU_TRY(cudaEventRecord(ev1, s.stream));
+    h->timing.grid_ctas = max_clus * pl.P;
+    if (pl.engine == 5) return MIXDIR_B200_OK;  // statistics already in place (atomics + last CTA)
     ReduceUnitsArgs r;
     r.NR = h->NR;
     r.NR2 = up.NR2;
@@ -1619,7 +1863,6 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
     k_reduce_units<<<dim3(h->NR, (pl.KP + 31) / 32), 256, 0, s.stream>>>(r);
     CU_TRY(cudaGetLastError());
     *launches += 1;
-    h->timing.grid_ctas = max_clus * pl.P;
   } else {
     CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
     if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
@@ -1703,12 +1946,20 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   h->timing.unit_pairs = pl.up.n_pairs;
   h->timing.unit_table_rows = pl.up.NR2;
 
+  // constants of the ELBO that depend on the hyper-parameters only (host libm; ~1 ulp from R's)
+  double termC_const = 0;
+  for (int j = 0; j < J; j++) termC_const += lgamma(h->ncat[j] * p->beta) - h->ncat[j] * lgamma(p->beta);
+  termC_const *= K;
+  const double termA_const = lgamma(K * p->alpha1) - K * lgamma(p->alpha1);
+
   // ---- initial state on every shard: class masses + table from phi_init ----
   auto iter_args = [&](Shard& s, int mode, bool poll) -> IterArgs {
     IterArgs ia;
     ia.J = J; ia.K = K; ia.KP = pl.KP; ia.dp = p->dp; ia.mode = mode;
-    ia.n_cat_bound = n_cat_bound; ia.NR = h->NR; ia.NR2 = pl.up.NR2; ia.stats_fixed = 0;
+    ia.n_cat_bound = n_cat_bound; ia.NR = h->NR; ia.NR2 = pl.up.NR2;
+    ia.stats_fixed = pl.engine == 5 ? 1 : 0;
     ia.beta = p->beta; ia.a1 = p->alpha1; ia.a2 = p->alpha2; ia.epsilon = p->epsilon;
+    ia.termC_const = termC_const; ia.termA_const = termA_const;
     ia.ncat = s.d_ncat; ia.rowoff = s.d_rowoff; ia.elem = s.d_elem; ia.erange = s.d_erange;
     ia.t2src = pl.up.identity ? nullptr : s.d_t2src;
     ia.stats = s.d_stats; ia.phi = s.d_phi; ia.T = s.d_T; ia.T2 = s.d_T2; ia.part = s.d_part;
@@ -1720,9 +1971,11 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   };
   for (auto& s : h->shards) {
     RET_IF(ensure_workspace(h, s, K, pl, p->max_iter));
-    RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096 + unit_stage_bytes(pl.up)));
+    RET_IF(pin_reset(s, (rag + K + J) * 8 + 4096 + unit_stage_bytes(pl.up) + seg_stage_bytes(pl.sp)));
     RET_IF(upload_ragoff(h, s, K));
     RET_IF(ensure_units(h, s, pl));
+    if (pl.engine == 5)  // the E+M kernel ADDS into the statistics; k_iter clears them after use
+      CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
     while ((int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreate(&e));
@@ -1774,7 +2027,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
       stat_bufs[si] = s.d_stats;
       if (si == 0) l0 += l;
     }
-    RET_IF(allreduce(h, stat_bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
+    RET_IF(allreduce_stats(h, stat_bufs, tab, pl));
     for (size_t si = 0; si < h->shards.size(); si++) {
       Shard& s = h->shards[si];
       CU_TRY(cudaSetDevice(s.device));
@@ -2110,9 +2363,10 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
   for (size_t si = 0; si < h->shards.size(); si++) {
     Shard& s = h->shards[si];
     RET_IF(ensure_workspace(h, s, K, pl, 1));
-    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096 + unit_stage_bytes(pl.up)));
+    RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096 + unit_stage_bytes(pl.up) + seg_stage_bytes(pl.sp)));
     RET_IF(upload_ragoff(h, s, K));
     RET_IF(ensure_units(h, s, pl));
+    if (pl.engine == 5) CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
@@ -2142,10 +2396,14 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     }
     bufs[si] = s.d_stats;
   }
-  RET_IF(allreduce(h, bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum));
+  RET_IF(allreduce_stats(h, bufs, tab, pl));
   {
     Shard& s = h->shards[0];
     CU_TRY(cudaSetDevice(s.device));
+    if (pl.engine == 5) {
+      k_fixed_to_double<<<64, 256, 0, s.stream>>>(s.d_stats, tab);
+      CU_TRY(cudaGetLastError());
+    }
     ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, nullptr, s.d_stats, 0, 0.0};
     k_table_to_ragged<<<jk_grid, 128, 0, s.stream>>>(ra, s.d_rag_b);
     CU_TRY(cudaGetLastError());

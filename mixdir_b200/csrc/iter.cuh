@@ -30,15 +30,17 @@ struct IterArgs {
                       // 1: full iteration step from the statistics buffer
   int n_cat_bound;    // loop bound of the digamma-sum (mixdir_impl.cpp:65 quirk)
   int NR, NR2;
-  int stats_fixed;    // 1: S and cs are int64 fixed point (scale 2^-31, k_em_seg); 0: doubles
+  int stats_fixed;    // 1: S is int64 fixed point (scale 2^-31, k_em_seg); 0: doubles
   double beta, a1, a2, epsilon;
+  double termC_const; // K * sum_j [lgamma(C_j beta) - C_j lgamma(beta)]: expec_log_ujk, R/mixdir_vi.R:172-174
+  double termA_const; // dp=0: lgamma(K alpha) - K lgamma(alpha), R/mixdir_vi.R:164-166
   const int* ncat;    // [J]
   const int* rowoff;  // [J]
   const int2* elem;   // [gridDim.x] (feature a, feature b or -1)
   const int2* erange; // [gridDim.x] (first unit-table row, rows) of the element; rows 0: no T2
   const int2* t2src;  // [NR2] feature-table rows a unit row is the sum of (null: identity plan)
-  double* stats;      // [S : NR*KP | cs : KP | H | underflow | nNA | bad]   (mode 1; S, cs zeroed
-                      //  after use when stats_fixed: the E+M kernel adds into them with atomics)
+  double* stats;      // [S : NR*KP | cs : KP | H | underflow | nNA | bad]   (mode 1; S zeroed after
+                      //  use when stats_fixed: the E+M kernel adds into it with atomics)
   double* phi;        // [NR][KP]
   double* T;          // [NR][KP]
   double* T2;         // [NR2][KP]
@@ -54,7 +56,7 @@ struct IterArgs {
 };
 
 __device__ __forceinline__ double stat_value(const IterArgs& a, size_t i) {
-  if (a.stats_fixed) return (double)reinterpret_cast<const long long*>(a.stats)[i] * 4.656612873077392578125e-10;
+  if (a.stats_fixed && i < (size_t)a.NR * a.KP) return (double)reinterpret_cast<const long long*>(a.stats)[i] * 4.656612873077392578125e-10;
   return a.stats[i];
 }
 
@@ -88,7 +90,7 @@ __device__ void prior_step(const IterArgs& a, const double* cs, double* red) {
         sE += (st->omega[k] - 1.0) * e;
       }
       for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
-      st->termA = lgamma(K * a.a1) - K * lgamma(a.a1) + sA;  // R/mixdir_vi.R:164-166
+      st->termA = a.termA_const + sA;                         // R/mixdir_vi.R:164-166
       st->termE = -lgamma(so) + sl - sE;                      // R/mixdir_vi.R:177-179
     }
   } else {
@@ -189,10 +191,7 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
       ds_bound[k] = dev_digamma(sum_bound);  // mixdir_impl.cpp:61-72
       ds_all[k] = dev_digamma(sum_all);      // R-level digamma(sum(phi_jk))
       a.T[g0 * KP + k] = 0.0;                // NA row
-      if (a.mode == 1) {
-        p0 += lgamma(C * a.beta) - C * lgamma(a.beta);  // expec_log_ujk, R/mixdir_vi.R:172-174
-        p2 -= lgamma(sum_all);                           // entrop_phi, R/mixdir_vi.R:190-192
-      }
+      if (a.mode == 1) p2 -= lgamma(sum_all);  // entrop_phi, R/mixdir_vi.R:190-192
     }
     __syncthreads();
     for (int i = tid; i < cells; i += nt) {
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
       }
       __syncthreads();
     }
-    const double tC = red[0], tG = red[2 * kIterThreads];
+    const double tC = red[0] + a.termC_const, tG = red[2 * kIterThreads];
     const double tD = red[kIterThreads] + (double)K * a.stats[tab + KP + 2];  // +1 per NA cell per class
     __syncthreads();
     // class masses of the new zeta, permuted: what the next prior is built from
@@ -311,9 +310,9 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
     }
     for (int k = tid; k < K; k += nt) a.cs_cur[k] = red[k];
     __syncthreads();
-    if (a.stats_fixed) {  // the next E+M pass adds into S and cs with atomics
+    if (a.stats_fixed) {  // the next E+M pass adds into S with atomics
       long long* z = reinterpret_cast<long long*>(a.stats);
-      for (size_t i = tid; i < tab + KP; i += nt) z[i] = 0;
+      for (size_t i = tid; i < tab; i += nt) z[i] = 0;
     }
   }
   prior_step(a, a.cs_cur, red);

@@ -39,10 +39,18 @@ constexpr int kRowPad = 512;      // zero rows appended to the code matrix
 // oracle_digamma) so that host and device agree to a few ulp.
 __device__ __forceinline__ double dev_digamma(double x) {
   if (!(x > 0.0)) return nan("");
+  // psi(x) = psi(x + n) - sum_{i<n} 1/(x+i), n = smallest integer with x + n >= 10.  The
+  // reciprocals are independent (the oracle's loop divides one after the other: same terms, same
+  // order of the additions).
   double acc = 0.0;
-  while (x < 10.0) {
-    acc -= 1.0 / x;
-    x += 1.0;
+  if (x < 10.0) {
+    const int n = (int)ceil(10.0 - x);
+    double r[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) r[i] = (i < n) ? 1.0 / (x + (double)i) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) acc -= r[i];
+    x += (double)n;
   }
   const double inv = 1.0 / x;
   const double inv2 = inv * inv;
@@ -416,15 +424,24 @@ __global__ void __launch_bounds__(256) k_reduce_units(ReduceUnitsArgs a) {
     a.stats[(size_t)g * a.KP + k] = t;
   }
   if (blockIdx.x == 0 && blockIdx.y == 0) {
-    for (int kk = threadIdx.x; kk < a.KP; kk += blockDim.x) {
+    // class masses: warp w takes classes w, w+8, ...; lanes take the clusters round-robin, then a
+    // fixed shuffle tree.  Entropy: 256 threads round-robin over the CTAs, then a fixed tree.
+    __syncthreads();
+    for (int kk = warp; kk < a.KP; kk += 8) {
       double t = 0;
-      for (int c = 0; c < a.n_clusters; c++) t += a.cspart[(size_t)c * a.KP + kk];
-      a.stats[n + kk] = t;
+      for (int c = lane; c < a.n_clusters; c += 32) t += a.cspart[(size_t)c * a.KP + kk];
+      t = warp_sum(t);
+      if (lane == 0) a.stats[n + kk] = t;
     }
+    double h = 0;
+    for (int c = threadIdx.x; c < a.n_ctas; c += 256) h += a.Hpart[c];
+    h = warp_sum(h);
+    if (lane == 0) part[0][warp] = h;
+    __syncthreads();
     if (threadIdx.x == 0) {
-      double h = 0;
-      for (int c = 0; c < a.n_ctas; c++) h += a.Hpart[c];
-      a.stats[n + a.KP] = h;
+      double t = 0;
+      for (int w = 0; w < 8; w++) t += part[0][w];
+      a.stats[n + a.KP] = t;
       a.stats[n + a.KP + 1] = (*a.underflow) ? 1.0 : 0.0;
       a.stats[n + a.KP + 2] = (double)a.scan->n_missing;
       a.stats[n + a.KP + 3] = a.scan->bad ? 1.0 : 0.0;

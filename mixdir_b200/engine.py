@@ -84,6 +84,9 @@ class Engine:
         if self.ncat.size != self.n_features:
             raise ValueError("len(ncat) != number of features")
         self._h = C.c_void_p()
+        # the upload is asynchronous (include/mixdir_b200.h): the source must stay alive and untouched
+        # until the first call that resolves it; keep it for the life of the handle
+        self._codes = codes
         ip = self.ncat.ctypes.data_as(C.POINTER(C.c_int))
         if dist is not None:
             self._comm = dist  # keep the communicator alive as long as the handle
@@ -102,6 +105,7 @@ class Engine:
         self = cls.__new__(cls)
         L = _capi.lib()
         X = np.asfortranarray(X, dtype=np.float64)
+        self._codes = X  # asynchronous upload: keep the source alive
         self.n_rows, self.n_features = X.shape
         self.ncat = np.ascontiguousarray(ncat, dtype=np.int32)
         self._h = C.c_void_p()
@@ -123,6 +127,7 @@ class Engine:
         if getattr(self, "_h", None) is not None and self._h:
             _capi.lib().mixdir_b200_destroy(self._h)
             self._h = C.c_void_p()
+            self._codes = None
 
     def __del__(self):
         try:
