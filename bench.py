@@ -211,6 +211,20 @@ def config_dict(args, ncat):
                          % (args.rows * args.features / 1e6)}
 
 
+def elbo_rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def r_matrix(codes):
+    """the fp64 column-major matrix mixdir() hands to mixdir_vi() (R/mixdir.R:117-118): 1..C_j, NA"""
+    X = np.empty(codes.shape, dtype=np.float64, order="F")
+    for j in range(codes.shape[1]):
+        X[:, j] = codes[:, j]
+    X[X == 0] = np.nan
+    return X
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -223,30 +237,20 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ncat = workload(args)
     K, J, N = args.k, args.features, args.rows
 
-    # ---- synthetic shard, generated on the device, kept in pinned host memory ----
-    dev_codes = synth.make_codes_torch(2, N, ncat, K, p_na=args.p_na, row0=rank * N,
-                                       device=f"cuda:{local}")
-    host_codes = torch.empty(dev_codes.shape, dtype=dev_codes.dtype, pin_memory=True)
-    host_codes.copy_(dev_codes)
-    del dev_codes
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
-    codes_np = host_codes.numpy()
-    if codes_np.dtype == np.int16:
-        codes_np = codes_np.view(np.uint16)
-
     uid = None
     if world > 1:
-        t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             t.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(t, 0)
         uid = bytes(t.cpu().numpy().tobytes())
+    comm = Comm(local, rank, world, uid)  # one NCCL communicator, shared by every handle below
 
     def barrier():
         if world > 1:
@@ -256,78 +260,178 @@ def run_ours(args):
     def maxr(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def pinned_shard(seed, rows, ncat_, K_, p_na, row0):
+        d = synth.make_codes_torch(seed, rows, ncat_, K_, p_na=p_na, row0=row0, device=dev)
+        hst = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
+        hst.copy_(d)
+        del d
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        a = hst.numpy()
+        return (a.view(np.uint16) if a.dtype == np.int16 else a), hst
+
+    def timed_fit(codes, ncat_, K_, rows_global, steps, warmup, engine=0):
+        """device-resident iterations: (ms per step max over ranks, E+M kernel ms per launch, timing, result)"""
+        cs = np.full(K_, rows_global / K_)
+        ph = synth.phi_init(2, ncat_, K_)
+        with Engine(codes, ncat_, dist=comm) as e:
+            if engine:
+                e.set_engine(engine)
+            e.fit(K_, cs, ph, max_iter=warmup, epsilon=-np.inf, want_class_prob=False, want_pred_class=False)
+            barrier()
+            r = e.fit(K_, cs, ph, max_iter=steps, epsilon=-np.inf, want_class_prob=False,
+                      want_pred_class=False)
+            barrier()
+            tm = e.timing()
+        assert r["n_iter"] == steps
+        return maxr(tm["fit_loop_ms"]) / steps, maxr(tm["em_kernel_ms"]) / max(tm["em_launches"], 1), tm, r
+
+    # ---- multi-GPU parity: the sharded path against one GPU on the same global data ----
+    parity = None
+    if world > 1:
+        n_par = 65536
+        pc_codes, _ = synth.make_codes(5, n_par, ncat, K, p_na=0.02)
+        z0 = synth.zeta_init(5, 4096, K).sum(axis=0) * (n_par / 4096.0)
+        ph0 = synth.phi_init(5, ncat, K)
+        lo, hi = n_par * rank // world, n_par * (rank + 1) // world
+        with Engine(np.ascontiguousarray(pc_codes[lo:hi]), ncat, dist=comm) as e:
+            rd = e.fit(K, z0, ph0, max_iter=3, epsilon=-np.inf, want_class_prob=False)
+            eng_d = e.timing()["engine"]
+        pcs = [torch.zeros(n_par // world, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(pcs, torch.from_numpy(rd["pred_class"]).to(dev))  # 65536 rows: equal shards
+        if rank == 0:
+            with Engine(pc_codes, ncat) as e:
+                rs = e.fit(K, z0, ph0, max_iter=3, epsilon=-np.inf, want_class_prob=False)
+                eng_s = e.timing()["engine"]
+            pc_all = torch.cat(pcs).cpu().numpy()
+            parity = {"rows": n_par, "iterations": 3, "engine_sharded": eng_d, "engine_single": eng_s,
+                      "elbo_max_rel_diff": elbo_rel(rd["convergence"], rs["convergence"]),
+                      "phi_max_abs_diff": float(np.max(np.abs(rd["phi"] - rs["phi"]))),
+                      "pred_class_identical": bool(np.array_equal(pc_all, rs["pred_class"])),
+                      "tolerance": "ELBO 1e-9 relative, pred_class identical"}
+            parity["ok"] = bool(parity["elbo_max_rel_diff"] < 1e-9 and parity["pred_class_identical"])
+        ok = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
+        dist.broadcast(ok, 0)
+        if int(ok.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", "parity_vs_single": parity}))
+            dist.destroy_process_group()
+            return 1
+
+    # ---- the headline workload: synthetic shard generated on the device, kept in pinned host memory ----
+    codes_np, _keep = pinned_shard(2, N, ncat, K, args.p_na, rank * N)
     cs0 = np.full(K, N * world / K)
     p0 = synth.phi_init(2, ncat, K)
     ncb = int(ncat.max())  # n_cat = max(X) (R/mixdir_vi.R:8): every category occurs in this data
-    comm = Comm(local, rank, world, uid)  # one NCCL communicator, shared by every handle below
-    mk = lambda: Engine(codes_np, ncat, dist=comm)  # noqa: E731
 
     # ---- value: device-resident, K iterations, CUDA events inside the engine ----
-    eng = mk()
-    if args.engine:
-        eng.set_engine(args.engine)
-    eng.fit(K, cs0, p0, max_iter=args.warmup, epsilon=-np.inf, want_class_prob=False,
-            want_pred_class=False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
     t0 = time.perf_counter()
-    res = eng.fit(K, cs0, p0, max_iter=args.steps, epsilon=-np.inf, want_class_prob=False,
-                  want_pred_class=False)
-    barrier()
+    ms_step, em_ms_launch, tm, res = timed_fit(codes_np, ncat, K, N * world, args.steps, args.warmup, args.engine)
     t1 = time.perf_counter()
-    tm = eng.timing()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    loop_ms = maxr(tm["fit_loop_ms"])
-    em_ms = maxr(tm["em_kernel_ms"])
-    ms_step = loop_ms / args.steps
     value = N * world * J / (ms_step * 1e-3)
-    assert res["n_iter"] == args.steps
 
-    # ---- final pass (reported separately) ----
-    _ = eng.predict(K, res["lambda_"], res["category_prob"], want_class_prob=False)  # loads the kernel
+    # ---- final pass (reported separately): pred_class only, then with class_prob ----
+    final = {}
+    with Engine(codes_np, ncat, dist=comm) as e:
+        e.predict(K, res["lambda_"], res["category_prob"], want_class_prob=False)  # loads the kernel, upload
+        barrier()
+        tp = time.perf_counter()
+        e.predict(K, res["lambda_"], res["category_prob"], want_class_prob=False)
+        barrier()
+        final["pred_class_ms"] = maxr((time.perf_counter() - tp) * 1e3)
+        final["pred_class_d2h_bytes"] = int(N * 4)
+        nsub = min(N, 200_000)
+    with Engine(codes_np[:nsub], ncat) as e:  # posterior peakedness (SURVEY 8d): mean max_k class_prob
+        cp, _ = e.predict(K, res["lambda_"], res["category_prob"])
+        peaked = float(cp.max(axis=1).mean())
+    if args.class_prob and rank == 0:  # the 2.56 GB class_prob read-back, once, one GPU
+        with Engine(codes_np, ncat) as e:
+            tp = time.perf_counter()
+            e.predict(K, res["lambda_"], res["category_prob"], want_pred_class=False)
+            final["class_prob_ms"] = (time.perf_counter() - tp) * 1e3
+            final["class_prob_d2h_bytes"] = int(N * K * 8)
     barrier()
-    tp = time.perf_counter()
-    _ = eng.predict(K, res["lambda_"], res["category_prob"], want_class_prob=False)
-    barrier()
-    predict_ms = (time.perf_counter() - tp) * 1e3
-    eng.close()
 
-    # ---- e2e: host buffers through the C ABI, upload + 1 iteration + read-back per step ----
+    # ---- e2e: what the R adapter does (r_adapter/): fp64 column-major matrix in pageable host memory ->
+    #      mixdir_b200_create_from_r_matrix + mixdir_b200_fit(1 iteration, pred_class read back) ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(1):
-        with mk() as e:
-            e.fit(K, cs0, p0, max_iter=1, epsilon=-np.inf, want_class_prob=False, want_pred_class=False,
-                  n_cat_bound=ncb)
+    X = r_matrix(codes_np)
+    step_ms, d2h = [], 0
+
+    def e2e_step_r():
+        ts = time.perf_counter()
+        with Engine.from_r_matrix(X, ncat, dist=comm if world > 1 else None) as e:
+            r = e.fit(K, cs0, p0, max_iter=1, epsilon=-np.inf, want_class_prob=False)
+        return (time.perf_counter() - ts) * 1e3, r
+
+    e2e_step_r()
+    for _ in range(e2e_steps):
+        barrier()
+        ms, r = e2e_step_r()
+        step_ms.append(ms)
+        d2h = (r["convergence"].nbytes + r["lambda_"].nbytes + r["phi"].nbytes + r["category_prob"].nbytes +
+               r["omega"].nbytes + r["pred_class"].nbytes + 32)
     barrier()
-    d2h = 0
-    step_ms = []
+    e2e_ms = maxr(statistics.median(step_ms))
+    e2e_value = N * world * J / (e2e_ms * 1e-3)
+    del X
+
+    # ---- e2e best case: packed u8 codes in page-locked memory, upload overlapped with the iteration,
+    #      no per-row result read back (round 1's e2e) ----
+    mk = lambda: Engine(codes_np, ncat, dist=comm)  # noqa: E731
+    with mk() as e:
+        e.fit(K, cs0, p0, max_iter=1, epsilon=-np.inf, want_class_prob=False, want_pred_class=False,
+              n_cat_bound=ncb)
+    best_ms = []
     for _ in range(e2e_steps):
         barrier()
         ts = time.perf_counter()
         with mk() as e:
-            tc = time.perf_counter()
-            r = e.fit(K, cs0, p0, max_iter=1, epsilon=-np.inf, want_class_prob=False,
-                      want_pred_class=False, n_cat_bound=ncb)
-            tf = time.perf_counter()
-        step_ms.append((time.perf_counter() - ts) * 1e3)
-        if os.environ.get("BENCH_DEBUG") and rank == 0:
-            print("e2e step: create %.2f fit %.2f destroy %.2f ms" % (
-                (tc - ts) * 1e3, (tf - tc) * 1e3, (time.perf_counter() - tf) * 1e3), file=sys.stderr)
-        d2h = r["convergence"].nbytes + r["lambda_"].nbytes + r["phi"].nbytes + \
-            r["category_prob"].nbytes + r["omega"].nbytes + 32
+            e.fit(K, cs0, p0, max_iter=1, epsilon=-np.inf, want_class_prob=False, want_pred_class=False,
+                  n_cat_bound=ncb)
+        best_ms.append((time.perf_counter() - ts) * 1e3)
     barrier()
-    # the host side of this box is shared: report the median step (mean and min beside it)
-    e2e_ms = maxr(statistics.median(step_ms))
-    e2e_mean, e2e_min = maxr(sum(step_ms) / len(step_ms)), maxr(min(step_ms))
-    e2e_value = N * world * J / (e2e_ms * 1e-3)
-    h2d = codes_np.nbytes + cs0.nbytes + p0.nbytes
+    best_e2e_ms = maxr(statistics.median(best_ms))
+
+    # ---- records beside the headline (SURVEY 8d/8e): p_NA = 0.1, strong scaling, the 8-GPU config ----
+    records = {}
+    if args.records:
+        if args.p_na == 0.0:
+            c2, k2 = pinned_shard(2, N, ncat, K, 0.10, rank * N)
+            ms2, em2, tm2, _ = timed_fit(c2, ncat, K, N * world, max(3, args.steps // 4), 3, args.engine)
+            records["p_na_0.1"] = {"ms_per_step": ms2, "value": N * world * J / (ms2 * 1e-3), "unit": UNIT,
+                                   "kernel_ms_per_launch": em2, "engine": tm2["engine"],
+                                   "unit_elements": tm2["unit_elements"], "feature_pairs": tm2["unit_pairs"]}
+            del c2, k2
+        if world > 1:
+            ns = N // world  # the SAME total rows as one GPU's workload, split over the ranks
+            ms3, em3, tm3, _ = timed_fit(codes_np[:ns], ncat, K, ns * world, args.steps, 3, args.engine)
+            records["strong"] = {"rows_total": ns * world, "rows_per_gpu": ns, "ms_per_step": ms3,
+                                 "value": ns * world * J / (ms3 * 1e-3), "unit": UNIT, "scaling": "strong",
+                                 "kernel_ms_per_launch": em3, "engine": tm3["engine"]}
+        if world == 8 or args.s5:
+            n5, j5, k5 = args.s5_rows, 100, 64
+            nc5 = np.array((C_PATTERN * 17)[:j5], dtype=np.int32)
+            c5, k5keep = pinned_shard(3, n5, nc5, k5, 0.0, rank * n5)
+            ms5, em5, tm5, _ = timed_fit(c5, nc5, k5, n5 * world, 5, 3, args.engine)
+            alg5 = n5 * j5
+            records["s5"] = {"workload": f"synthetic {n5} x {j5} per GPU ({n5 * world} x {j5} total), K={k5}: "
+                                         "BASELINE.json configs[4]",
+                             "ms_per_step": ms5, "value": n5 * world * j5 / (ms5 * 1e-3), "unit": UNIT,
+                             "kernel_ms_per_launch": em5, "engine": tm5["engine"],
+                             "classes_per_cta": tm5["classes_per_cta"], "cluster_size": tm5["cluster_size"],
+                             "grid_ctas": tm5["grid_ctas"],
+                             "roofline_frac_hbm": alg5 / (em5 * 1e-3) / 1e9 / hbm_peak()[0]}
+            del c5, k5keep
 
     if rank != 0:
         if world > 1:
@@ -337,37 +441,40 @@ def run_ours(args):
     peak, peak_src = hbm_peak()
     cb = codes_np.dtype.itemsize
     alg_bytes = N * J * cb  # per launch, per GPU: each code read once
-    em_ms_launch = em_ms / max(tm["em_launches"], 1)
     achieved = alg_bytes / (em_ms_launch * 1e-3) / 1e9
     traffic = ncu_traffic()
+    same_shape = bool(traffic and tm["engine"] == traffic.get("engine") and J == 60 and K == 32)
     cpu_val, cpu_kind, cpu_dt = cpu_reference_iteration(ncat, K, args.cpu_rows, 2)
+    kernel = {2: "k_em_fused", 4: "k_em_units", 5: "k_em_seg"}.get(tm["engine"], "k_em_generic")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, ncat),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(codes_np.nbytes + cs0.nbytes + p0.nbytes),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "ms_per_step_mean": e2e_mean, "ms_per_step_min": e2e_min,
-                "what": "mixdir_b200_create_dist(host codes, pinned; asynchronous chunked upload) + "
-                        "mixdir_b200_fit(max_iter=1; consumes the chunks as they land) + result "
-                        "read-back + mixdir_b200_destroy, per step"},
+                "ms_per_step_min": maxr(min(step_ms)), "host_input_bytes_per_step": int(N * J * 8),
+                "what": "per step: mixdir_b200_create_from_r_matrix on the reference's own X (fp64, column-major, "
+                        "PAGEABLE host memory: what r_adapter/ passes; packed to 1-byte codes by host threads "
+                        "inside the library, the packed bytes are what crosses PCIe) + mixdir_b200_fit(max_iter=1, "
+                        "n_cat from the upload scan) + final pass + pred_class read back + destroy"
+                        + ("" if world == 1 else " [one process per GPU: mixdir_b200_create_dist_from_r_matrix]")},
+        "e2e_best_case": {"value": N * world * J / (best_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": best_e2e_ms,
+                          "what": "packed u8 codes in page-locked host memory, chunked upload overlapped with "
+                                  "the iteration (n_cat passed by the caller), no per-row results read back"},
         "gpu_launches": int(tm["total_launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": (int(traffic["dram_bytes_per_row"] * N) if traffic and
-                                 tm["engine"] == traffic.get("engine", 2) and J == 60 and K == 32
-                                 else None),
-                     "traffic_source": (traffic or {}).get("source"),
-                     "kernel": {2: "k_em_fused", 4: "k_em_units", 5: "k_em_seg"}.get(tm["engine"],
-                                                                                       "k_em_generic"),
+                     "traffic": int(traffic["dram_bytes_per_row"] * N) if same_shape else None,
+                     "traffic_source": (traffic or {}).get("source") if same_shape else None,
+                     "kernel": kernel,
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel_ms_per_launch": em_ms_launch, "peak_source": peak_src,
-                     "kernel_share_of_step": em_ms / loop_ms,
+                     "kernel_share_of_step": em_ms_launch / ms_step,
                      "shared_memory": shared_memory_roofline(traffic, tm, N, J, K, em_ms_launch, clocks),
-                     "note": "shared-memory bound, not HBM bound: see DESIGN.md 4.1 (per code, K fp64 "
-                             "table gathers + K fp64 histogram read-modify-writes; the shared-memory "
-                             "pipe runs at ~81 % of its wavefront peak, profiles/README.md)"},
+                     "note": "not HBM bound: per code the pass does K fp64 table gathers from shared memory and "
+                             "K fixed-point accumulations; it is bound by shared-memory bandwidth and instruction "
+                             "issue (DESIGN.md 4.1, profiles/README.md)"},
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": f"{args.cpu_rows} rows x {J} features, K={K}, 2 iterations "
                                    f"({cpu_dt:.2f} s/iter), same generator as the GPU workload; "
@@ -378,7 +485,11 @@ def run_ours(args):
                    "cluster_size": tm["cluster_size"], "grid_ctas": tm["grid_ctas"],
                    "smem_bytes": tm["smem_bytes"], "unit_elements": tm["unit_elements"],
                    "feature_pairs": tm["unit_pairs"], "unit_table_rows": tm["unit_table_rows"]},
-        "final_pass_ms": predict_ms,
+        "final_pass": final,
+        "posterior_peakedness": {"mean_max_class_prob": peaked, "rows": nsub,
+                                 "at": f"parameters after {args.steps} iterations from the seeded start"},
+        "records": records,
+        "parity_vs_single": parity,
         "elbo_last": float(res["convergence"][-1]),
         "wall_ms_per_step": (t1 - t0) * 1e3 / args.steps,
     }
@@ -402,6 +513,12 @@ def main():
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
     ap.add_argument("--cpu-rows", dest="cpu_rows", type=int, default=20000)
+    ap.add_argument("--no-records", dest="records", action="store_false",
+                    help="skip the records beside the headline (p_NA=0.1, strong scaling, the 8-GPU config)")
+    ap.add_argument("--no-class-prob", dest="class_prob", action="store_false",
+                    help="skip timing the class_prob (N x K fp64) read-back")
+    ap.add_argument("--s5", action="store_true", help="run the 8-GPU BASELINE config's per-GPU shape at any --gpus")
+    ap.add_argument("--s5-rows", dest="s5_rows", type=int, default=25_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -19,7 +19,7 @@ WARN_ELBO_DECREASED, WARN_DP_LAST_COMPONENT = 1, 2
 SYMBOLS = [
     "mixdir_b200_ragged_size", "mixdir_b200_create", "mixdir_b200_create_from_r_matrix",
     "mixdir_b200_nccl_unique_id", "mixdir_b200_comm_init", "mixdir_b200_comm_destroy",
-    "mixdir_b200_create_dist", "mixdir_b200_destroy", "mixdir_b200_release_cache",
+    "mixdir_b200_create_dist", "mixdir_b200_create_dist_from_r_matrix", "mixdir_b200_destroy", "mixdir_b200_release_cache",
     "mixdir_b200_n_rows", "mixdir_b200_max_code", "mixdir_b200_n_missing", "mixdir_b200_fit",
     "mixdir_b200_predict", "mixdir_b200_feature_divergence", "mixdir_b200_estep",
     "mixdir_b200_last_timing",
@@ -64,6 +64,7 @@ def lib():
     L.mixdir_b200_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.mixdir_b200_comm_destroy.argtypes = [vp]
     L.mixdir_b200_create_dist.argtypes = [vp, C.c_int, C.c_int64, C.c_int, ip, vp, C.POINTER(vp)]
+    L.mixdir_b200_create_dist_from_r_matrix.argtypes = [vp, C.c_int64, C.c_int, ip, vp, C.POINTER(vp)]
     L.mixdir_b200_destroy.argtypes = [vp]
     L.mixdir_b200_n_rows.restype = C.c_int64
     L.mixdir_b200_n_rows.argtypes = [vp]

@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -234,7 +235,6 @@ struct Shard {
   size_t up_seen = 0;           // chunks already waited for + scanned on the compute stream
   ScanOut* d_scan = nullptr;    // NA count / largest code / validity, accumulated over chunks
   unsigned int* d_na_feat = nullptr;  // [J] NA cells per feature (null: J too large to count)
-  double* d_stage[2] = {nullptr, nullptr};  // fp64 staging of create_from_r_matrix
   // page-locked, device-mapped scratch for the small per-fit inputs: kernels pull them over
   // PCIe themselves, so they do not queue behind the bulk upload on the H2D copy engine
   unsigned char* h_pin = nullptr;
@@ -423,7 +423,7 @@ static void free_shard(Shard& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
   free_workspace(s);
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
-  dfree(s.d_ragoff); dfree(s.d_scan); dfree(s.d_stage[0]); dfree(s.d_stage[1]);
+  dfree(s.d_ragoff); dfree(s.d_scan);
   dfree(s.d_na_feat);
   dfree(s.d_udesc); dfree(s.d_ugbase); dfree(s.d_t2src); dfree(s.d_marg); dfree(s.d_ucodes);
   dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
@@ -566,30 +566,101 @@ static int upload_codes(mixdir_b200_handle* h, Shard& s, const uint8_t* src_rows
   return MIXDIR_B200_OK;
 }
 
-// Same for the reference's fp64 column-major matrix: copy a row block into one of two staging
-// buffers, pack it to codes on the copy stream, signal the chunk.
+// Same for the reference's fp64 column-major matrix (what mixdir() hands to mixdir_vi(),
+// R/mixdir.R:117-118): the codes are packed ON THE HOST, by a few threads, into page-locked staging
+// buffers (fp64 column-major -> 1- or 2-byte row-major: 8x fewer bytes cross PCIe than copying the
+// doubles, and a pageable 4.8 GB source would otherwise crawl through the driver's bounce buffers),
+// each chunk is sent as soon as it is packed.  Invalid cells (not NA and not a positive integer
+// code) raise the scan's `bad` flag.  MIXDIR_B200_HOST_THREADS overrides the thread count.
+static int host_pack_threads() {
+  if (const char* e = getenv("MIXDIR_B200_HOST_THREADS")) {
+    const int t = atoi(e);
+    if (t >= 1) return std::min(t, 64);
+  }
+  const unsigned hc = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+}
+
+template <typename CT>
+static void pack_block(const double* X, int64_t ld, int64_t r0, int64_t r1, int J, int row_bytes,
+                       unsigned char* dst /* row r0 of the chunk buffer */, int limit, int* bad) {
+  constexpr int64_t RB = 256;  // rows per block: 256 x J codes stay in L1 while the columns stream
+  int b = 0;
+  for (int64_t i0 = r0; i0 < r1; i0 += RB) {
+    const int64_t n = std::min(RB, r1 - i0);
+    for (int j = 0; j < J; j++) {
+      const double* col = X + (int64_t)j * ld + i0;
+      unsigned char* out = dst + (i0 - r0) * row_bytes + (size_t)j * sizeof(CT);
+      for (int64_t i = 0; i < n; i++) {
+        const double v = col[i];
+        int x = 0;
+        if (v == v) {  // not NA / NaN
+          x = (int)v;
+          if (v < 1.0 || v != (double)x || x > limit) {
+            b = 1;
+            x = 0;
+          }
+        }
+        *reinterpret_cast<CT*>(out + i * row_bytes) = (CT)x;
+      }
+    }
+  }
+  if (b) __atomic_store_n(bad, 1, __ATOMIC_RELAXED);
+}
+
 static int upload_r_matrix(mixdir_b200_handle* h, Shard& s, const double* X, int64_t ld) {
   if (s.n_rows == 0) return MIXDIR_B200_OK;
   const int J = h->J;
-  const int64_t chunk = std::min<int64_t>(upload_chunk_rows(s.n_rows), 1 << 20);
-  RET_IF(dalloc(&s.d_stage[0], (size_t)chunk * J));
-  RET_IF(dalloc(&s.d_stage[1], (size_t)chunk * J));
-  int c = 0;
-  for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk, c++) {
-    const int64_t nr = std::min(chunk, s.n_rows - r0);
-    double* st = s.d_stage[c & 1];
-    CU_TRY(cudaMemcpy2DAsync(st, nr * sizeof(double), X + s.row0 + r0, ld * sizeof(double),
-                             nr * sizeof(double), J, cudaMemcpyHostToDevice, s.copy_stream));
-    uint8_t* dst = s.d_codes + (size_t)r0 * h->row_bytes;
-    const int grid = s.sm_count * 8;
-    if (h->CB == 1)
-      k_pack_r_matrix<1><<<grid, 256, 0, s.copy_stream>>>(st, nr, nr, J, dst, h->row_bytes, &s.d_scan->bad);
-    else
-      k_pack_r_matrix<2><<<grid, 256, 0, s.copy_stream>>>(st, nr, nr, J, dst, h->row_bytes, &s.d_scan->bad);
-    CU_TRY(cudaGetLastError());
-    RET_IF(push_chunk_event(s, r0 + nr));
+  const int64_t chunk = upload_chunk_rows(s.n_rows);
+  const size_t cbytes = (size_t)chunk * h->row_bytes;
+  unsigned char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t sent[2] = {nullptr, nullptr};
+  int bad = 0, status = MIXDIR_B200_OK;
+  auto body = [&]() -> int {
+    for (int b = 0; b < 2; b++) {
+      CU_TRY(cache::pin_get((void**)&stage[b], cbytes));
+      CU_TRY(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
+    }
+    const int T = host_pack_threads();
+    const int limit = h->CB == 1 ? 255 : 65535;
+    int c = 0;
+    for (int64_t r0 = 0; r0 < s.n_rows; r0 += chunk, c++) {
+      const int64_t nr = std::min(chunk, s.n_rows - r0);
+      unsigned char* st = stage[c & 1];
+      if (c >= 2) CU_TRY(cudaEventSynchronize(sent[c & 1]));  // its previous copy has left the buffer
+      if (h->J * h->CB != h->row_bytes) memset(st, 0, (size_t)nr * h->row_bytes);  // row padding bytes
+      std::vector<std::thread> pool;
+      const int64_t per = ((nr + T - 1) / T + 255) / 256 * 256;
+      for (int t = 0; t < T; t++) {
+        const int64_t a = std::min<int64_t>(nr, t * per), b2 = std::min<int64_t>(nr, (t + 1) * per);
+        if (a >= b2) break;
+        const double* Xs = X + s.row0 + r0;
+        unsigned char* d = st + (size_t)a * h->row_bytes;
+        if (h->CB == 1)
+          pool.emplace_back(pack_block<uint8_t>, Xs, ld, a, b2, J, h->row_bytes, d, limit, &bad);
+        else
+          pool.emplace_back(pack_block<uint16_t>, Xs, ld, a, b2, J, h->row_bytes, d, limit, &bad);
+      }
+      for (auto& th : pool) th.join();
+      CU_TRY(cudaMemcpyAsync(s.d_codes + (size_t)r0 * h->row_bytes, st, (size_t)nr * h->row_bytes,
+                             cudaMemcpyHostToDevice, s.copy_stream));
+      CU_TRY(cudaEventRecord(sent[c & 1], s.copy_stream));
+      RET_IF(push_chunk_event(s, r0 + nr));
+    }
+    if (bad) {  // seen by the upload scan's consumers (k_em_*, resolve_scan)
+      static const int one = 1;
+      CU_TRY(cudaMemcpyAsync(&s.d_scan->bad, &one, sizeof(int), cudaMemcpyHostToDevice, s.copy_stream));
+      RET_IF(push_chunk_event(s, s.n_rows));
+    }
+    CU_TRY(cudaStreamSynchronize(s.copy_stream));  // the staging buffers go back to the cache
+    return MIXDIR_B200_OK;
+  };
+  status = body();
+  for (int b = 0; b < 2; b++) {
+    if (sent[b]) cudaEventDestroy(sent[b]);
+    if (stage[b]) cache::pin_put(stage[b]);
   }
-  return MIXDIR_B200_OK;
+  return status;
 }
 
 // make upload chunks [s.up_seen, upto] visible to the compute stream and scan them
@@ -639,8 +710,6 @@ static int resolve_scan(mixdir_b200_handle* h) {
                              cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
     for (int j = 0; j < h->J; j++) na_any[j] += s.d_na_feat ? (long long)(na_cnt[j] != 0) : 1;
-    dfree(s.d_stage[0]);
-    dfree(s.d_stage[1]);
     miss += (int64_t)o.n_missing;
     mx = std::max(mx, o.max_code);
     bad |= o.bad;
@@ -850,6 +919,45 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
     s.owns_comm = false;
     RET_IF(init_shard_static(h, s));
     return upload_codes(h, s, (const uint8_t*)codes_local);
+  };
+  if (st == MIXDIR_B200_OK) st = body();
+  if (st != MIXDIR_B200_OK) {
+    std::string keep = g_err;
+    mixdir_b200_destroy(h);
+    g_err = keep;
+    return st;
+  }
+  *out = h;
+  return MIXDIR_B200_OK;
+}
+
+extern "C" int mixdir_b200_create_dist_from_r_matrix(const double* X_local, int64_t n_rows_local,
+                                                     int n_features, const int* ncat,
+                                                     mixdir_b200_comm* comm, mixdir_b200_handle** out) {
+  if (!out) return fail(MIXDIR_B200_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (!comm) return fail(MIXDIR_B200_BAD_ARGUMENT, "comm is NULL");
+  if (n_rows_local < 0 || (n_rows_local > 0 && !X_local)) return fail(MIXDIR_B200_BAD_ARGUMENT, "X_local is NULL");
+  if (!ncat || n_features < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "bad ncat / n_features");
+  int cb = 1;
+  for (int j = 0; j < n_features; j++)
+    if (ncat[j] > 255) cb = 2;
+  DeviceGuard guard;
+  mixdir_b200_handle* h = new mixdir_b200_handle();
+  h->rank = comm->rank;
+  h->world = comm->world;
+  int st = init_geometry(h, cb, n_features, ncat);
+  auto body = [&]() -> int {
+    h->n_rows = n_rows_local;
+    h->shards.resize(1);
+    Shard& s = h->shards[0];
+    s.device = comm->device;
+    s.row0 = 0;
+    s.n_rows = n_rows_local;
+    s.comm = comm->comm;
+    s.owns_comm = false;
+    RET_IF(init_shard_static(h, s));
+    return upload_r_matrix(h, s, X_local, n_rows_local);
   };
   if (st == MIXDIR_B200_OK) st = body();
   if (st != MIXDIR_B200_OK) {

@@ -145,32 +145,6 @@ __global__ void k_scan_codes(const uint8_t* __restrict__ codes, int row_bytes, i
   }
 }
 
-// fp64 column-major R matrix (NaN = NA) chunk -> packed row-major codes.
-// X chunk: rows [r0, r0+nr) of an n_total x J column-major matrix already on device.
-template <int CB>
-__global__ void k_pack_r_matrix(const double* __restrict__ X, int64_t ld, int64_t nr, int J,
-                                uint8_t* __restrict__ codes, int row_bytes, int* bad) {
-  const int64_t total = nr * J;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total;
-       c += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(c / nr);
-    const int64_t i = c - (int64_t)j * nr;  // consecutive threads -> consecutive rows (coalesced read)
-    const double v = X[i + (int64_t)j * ld];
-    int x = 0;
-    if (!isnan(v)) {
-      x = (int)v;
-      if (v < 1.0 || v != (double)x || x > (CB == 1 ? 255 : 65535)) {
-        *bad = 1;
-        x = 0;
-      }
-    }
-    if (CB == 1)
-      codes[i * row_bytes + j] = (uint8_t)x;
-    else
-      reinterpret_cast<uint16_t*>(codes + i * row_bytes)[j] = (uint16_t)x;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // prior step: omega / kappa from the class masses of the previous zeta, the
 // per-class prior logit, and the ELBO terms that depend on omega/kappa only.

@@ -100,20 +100,26 @@ class Engine:
         _check(st)
 
     @classmethod
-    def from_r_matrix(cls, X, ncat, devices=None):
-        """X: [N, J] float64, values 1..C_j, NaN = NA (the matrix mixdir() builds, R/mixdir.R:117-118)."""
+    def from_r_matrix(cls, X, ncat, devices=None, dist=None):
+        """X: [N, J] float64, values 1..C_j, NaN = NA (the matrix mixdir() builds, R/mixdir.R:117-118).
+        dist: a Comm for the one-process-per-GPU flavour (X = this rank's rows)."""
         self = cls.__new__(cls)
         L = _capi.lib()
         X = np.asfortranarray(X, dtype=np.float64)
-        self._codes = X  # asynchronous upload: keep the source alive
+        self._codes = None  # the library has packed and copied X when create returns
         self.n_rows, self.n_features = X.shape
         self.ncat = np.ascontiguousarray(ncat, dtype=np.int32)
         self._h = C.c_void_p()
-        dev = None if devices is None else (C.c_int * len(devices))(*devices)
-        st = L.mixdir_b200_create_from_r_matrix(_ptr(X), self.n_rows, self.n_features,
-                                                self.ncat.ctypes.data_as(C.POINTER(C.c_int)),
-                                                0 if devices is None else len(devices), dev,
-                                                C.byref(self._h))
+        ip = self.ncat.ctypes.data_as(C.POINTER(C.c_int))
+        if dist is not None:
+            self._comm = dist
+            st = L.mixdir_b200_create_dist_from_r_matrix(_ptr(X), self.n_rows, self.n_features, ip,
+                                                         dist._c, C.byref(self._h))
+        else:
+            dev = None if devices is None else (C.c_int * len(devices))(*devices)
+            st = L.mixdir_b200_create_from_r_matrix(_ptr(X), self.n_rows, self.n_features, ip,
+                                                    0 if devices is None else len(devices), dev,
+                                                    C.byref(self._h))
         _check(st)
         return self
 
