@@ -578,7 +578,7 @@ static int host_pack_threads() {
     if (t >= 1) return std::min(t, 64);
   }
   const unsigned hc = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+  return (int)std::max(1u, std::min(16u, hc ? hc : 1u));
 }
 
 template <typename CT>
@@ -672,6 +672,7 @@ static int consume_upload(mixdir_b200_handle* h, Shard& s, size_t upto) {
     CU_TRY(cudaStreamWaitEvent(s.stream, s.up_ev[c], 0));
     const int64_t r0 = c == 0 ? 0 : s.up_end[c - 1];
     const int64_t nr = s.up_end[c] - r0;
+    if (nr <= 0) continue;  // a marker behind the last chunk (invalid cells found by the host packer)
     const uint8_t* base = s.d_codes + (size_t)r0 * h->row_bytes;
     const int grid = (int)std::min<int64_t>(s.sm_count * 8, (nr * h->WPR + 255) / 256);
     const size_t sm = s.d_na_feat ? (size_t)h->J * sizeof(unsigned int) : 0;
