@@ -169,6 +169,29 @@ int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_params* params,
                     double* prior_param, double* phi, double* category_prob,
                     double* class_prob, int32_t* pred_class, int* warn_flags);
 
+/* ---- repetitions: several fits of one batch ----------------------------------
+ * Replaces: the `repetitions` loop of mixdir() (R/mixdir.R:120-134): n_fits independent restarts
+ * on the same data and hyper-parameters, each from its own initial values, the result with the
+ * largest ELBO kept (`if(result$ELBO < result_tmp$ELBO) result <- result_tmp`: the FIRST maximum).
+ * Small fits are bound by launch latency, not by the GPU, so the library runs up to 8 of them
+ * concurrently (one CUDA stream, workspace and host thread each, all reading the ONE uploaded code
+ * matrix; MIXDIR_B200_BATCH_STREAMS overrides the number); a fit whose row pass fills the GPU
+ * (> 2M rows), and any multi-GPU handle, runs its restarts one after the other.  Every fit is
+ * bit-identical to the same mixdir_b200_fit call made alone.
+ *   colsum_init [n_fits][K], phi_init [n_fits][ragged]            inputs, fit after fit
+ *   elbo_trace  [n_fits][max(max_iter,1)] (nullable), n_iter / converged / warn_flags / status
+ *   [n_fits] (nullable), elbo [n_fits], lambda [n_fits][K], prior_param [n_fits][K or 2K] (nullable),
+ *   phi (nullable) / category_prob [n_fits][ragged]               outputs, fit after fit
+ *   best        index of the kept fit (-1 on error)
+ *   class_prob, pred_class (nullable)  of the kept fit only, computed from its lambda and
+ *               category_prob as predict_class does (R/predict.R:88-103 == R/mixdir_vi.R:136-148)
+ * Returns the status of the first failed fit (an error in any repetition ends mixdir()), else OK. */
+int mixdir_b200_fit_batch(mixdir_b200_handle* h, const mixdir_b200_fit_params* params, int n_fits,
+                          const double* colsum_init, const double* phi_init, double* elbo_trace,
+                          int* n_iter, int* converged, double* elbo, double* lambda,
+                          double* prior_param, double* phi, double* category_prob, int* warn_flags,
+                          int* status, int* best, double* class_prob, int32_t* pred_class);
+
 /* ---- predict --------------------------------------------------------------
  * Replaces: the arithmetic of predict_class() (R/predict.R:88-103), identical to
  * the final pass of the drivers (R/mixdir_vi.R:136-148).  The handle holds the
@@ -188,8 +211,8 @@ int mixdir_b200_predict(mixdir_b200_handle* h, int n_latent, const double* lambd
  *   table          ragged T[j][k][r] = psi(phi_jkr) - psi(sum_r phi_jkr)
  *   S (ragged), colsum[K], entropy, underflow: the statistics buffer
  *   zeta (nullable) n_rows x K column-major normalised responsibilities
- *   engine         0 = automatic, 1 = generic kernel, 2 = fused kernel, 3 = bucketed fused kernel,
- *                  4 = unit kernel (1-byte codes) */
+ *   engine         0 = automatic, 1 = generic kernel, 2 = fused kernel, 4 = unit kernel (1-byte
+ *                  codes), 5 = sorted-segment kernel (1-byte codes; S is then exact in units of 2^-31) */
 int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const double* log_prior,
                       const double* table, int engine, double* S, double* colsum,
                       double* entropy, int* underflow, double* zeta);
@@ -201,8 +224,8 @@ typedef struct mixdir_b200_timing {
   int iterations;       /* iterations executed */
   int em_launches;      /* E+M kernel launches in the loop */
   int total_launches;   /* all kernel launches of the library inside the loop (per device) */
-  int engine;           /* 1 generic, 2 fused (k_em_fused), 3 bucketed fused (k_em_bucket),
-                           4 unit kernel (k_em_units) */
+  int engine;           /* 1 generic, 2 fused (k_em_fused), 4 unit kernel (k_em_units),
+                           5 sorted-segment kernel (k_em_seg) */
   int classes_per_cta;  /* fused: KC */
   int cluster_size;     /* fused: P */
   int grid_ctas;        /* fused: CTAs launched */
@@ -229,9 +252,10 @@ int mixdir_b200_feature_divergence(mixdir_b200_handle* h, int n_latent, const do
                                    int measure, const int64_t* rows, int64_t n_rows_sub, double* out);
 
 int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_timing* out);
-/* 0 = automatic (default: unit kernel for 1-byte codes, else fused, else bucketed, else generic),
- * 1 = generic kernel only, 2 = fused kernel or fail, 3 = bucketed fused kernel or fail,
- * 4 = unit kernel or fail */
+/* 0 = automatic (default: 1-byte codes: the sorted-segment kernel from 16384 rows per shard on, else
+ * the unit kernel; 2-byte codes: the fused kernel; the generic kernel where none of them fits),
+ * 1 = generic kernel only, 2 = fused kernel or fail, 4 = unit kernel or fail,
+ * 5 = sorted-segment kernel or fail */
 int mixdir_b200_set_engine(mixdir_b200_handle* h, int engine);
 /* Feature pairing of the fused and unit kernels (default on): two features share one table gather and one
  * histogram update where shared memory allows.  Results change only by floating-point

@@ -21,6 +21,7 @@ SYMBOLS = [
     "mixdir_b200_nccl_unique_id", "mixdir_b200_comm_init", "mixdir_b200_comm_destroy",
     "mixdir_b200_create_dist", "mixdir_b200_create_dist_from_r_matrix", "mixdir_b200_destroy", "mixdir_b200_release_cache",
     "mixdir_b200_n_rows", "mixdir_b200_max_code", "mixdir_b200_n_missing", "mixdir_b200_fit",
+    "mixdir_b200_fit_batch",
     "mixdir_b200_predict", "mixdir_b200_feature_divergence", "mixdir_b200_estep",
     "mixdir_b200_last_timing",
     "mixdir_b200_set_engine", "mixdir_b200_set_pairing", "mixdir_b200_unit_plan", "mixdir_b200_unit_layout",
@@ -73,6 +74,8 @@ def lib():
     L.mixdir_b200_n_missing.argtypes = [vp]
     L.mixdir_b200_fit.argtypes = [vp, C.POINTER(FitParams), vp, vp, vp, ip, ip, dp, vp, vp, vp, vp,
                                   vp, vp, ip]
+    L.mixdir_b200_fit_batch.argtypes = [vp, C.POINTER(FitParams), C.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                        vp, vp, vp, vp, vp, ip, vp, vp]
     L.mixdir_b200_predict.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.mixdir_b200_feature_divergence.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int64, vp]
     L.mixdir_b200_estep.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, dp, ip, vp]

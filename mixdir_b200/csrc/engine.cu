@@ -180,6 +180,7 @@ struct Plan {
 
 struct Shard {
   int device = 0;
+  bool view = false;  // shares the uploaded data of another handle's shard (mixdir_b200_fit_batch)
   cudaStream_t stream = nullptr;
   int64_t row0 = 0, n_rows = 0;
   uint8_t* d_codes = nullptr;
@@ -257,6 +258,9 @@ struct mixdir_b200_handle {
   bool scan_resolved = false;
   bool bad = false;  // the upload scan found an invalid code: every later call reports it
   mixdir_b200_timing timing = {};
+  // mixdir_b200_fit_batch: handles that share this one's uploaded data, each with its own stream and
+  // workspace, one per concurrent fit (kept for later batches, freed with the handle)
+  std::vector<mixdir_b200_handle*> views;
 };
 
 static bool needs_allreduce(const mixdir_b200_handle* h) {
@@ -422,6 +426,10 @@ static void free_shard(Shard& s) {
   if (s.copy_stream) cudaStreamSynchronize(s.copy_stream);
   if (s.stream) cudaStreamSynchronize(s.stream);
   free_workspace(s);
+  if (s.view) {  // the data belongs to the parent handle
+    s.d_codes = nullptr; s.d_ncat = nullptr; s.d_rowoff = nullptr; s.d_rowoff_pad = nullptr;
+    s.d_scan = nullptr; s.d_na_feat = nullptr;
+  }
   dfree(s.d_codes); dfree(s.d_ncat); dfree(s.d_rowoff); dfree(s.d_rowoff_pad);
   dfree(s.d_ragoff); dfree(s.d_scan);
   dfree(s.d_na_feat);
@@ -778,6 +786,8 @@ static int make_shards(mixdir_b200_handle* h, int64_t n_rows, int n_devices, con
 extern "C" int mixdir_b200_destroy(mixdir_b200_handle* h) {
   if (!h) return MIXDIR_B200_OK;
   DeviceGuard guard;
+  for (auto* v : h->views) mixdir_b200_destroy(v);
+  h->views.clear();
   for (auto& s : h->shards) free_shard(s);
   delete h;
   return MIXDIR_B200_OK;
@@ -2219,6 +2229,143 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   }
   if (warn_flags) *warn_flags = warn;
   if (class_prob || pred_class) RET_IF(run_predict(h, K, pl.KP, class_prob, pred_class));
+  return MIXDIR_B200_OK;
+}
+
+// A handle that SHARES the uploaded data of `h` (one shard, upload resolved) and owns a stream and
+// a workspace: one concurrent fit of mixdir_b200_fit_batch.
+static int make_view(mixdir_b200_handle* h, mixdir_b200_handle** out) {
+  const Shard& ps = h->shards[0];
+  mixdir_b200_handle* v = new mixdir_b200_handle();
+  v->J = h->J; v->CB = h->CB; v->row_bytes = h->row_bytes; v->WPR = h->WPR; v->NR = h->NR;
+  v->n_rows = h->n_rows; v->n_missing = h->n_missing; v->max_code = h->max_code;
+  v->sum_ncat = h->sum_ncat;
+  v->ncat = h->ncat; v->rowoff = h->rowoff; v->rowoff_pad = h->rowoff_pad; v->ragoff1 = h->ragoff1;
+  v->has_na = h->has_na;
+  v->engine_pref = h->engine_pref; v->pairing = h->pairing;
+  v->scan_resolved = true; v->bad = h->bad;
+  v->shards.resize(1);
+  Shard& s = v->shards[0];
+  s.view = true;
+  s.device = ps.device; s.row0 = ps.row0; s.n_rows = ps.n_rows;
+  s.sm_count = ps.sm_count; s.smem_optin = ps.smem_optin;
+  s.d_codes = ps.d_codes; s.d_ncat = ps.d_ncat; s.d_rowoff = ps.d_rowoff;
+  s.d_rowoff_pad = ps.d_rowoff_pad; s.d_scan = ps.d_scan; s.d_na_feat = ps.d_na_feat;
+  auto body = [&]() -> int {
+    CU_TRY(cudaSetDevice(s.device));
+    CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&s.ev_loop0));
+    CU_TRY(cudaEventCreate(&s.ev_loop1));
+    CU_TRY(cache::pin_get((void**)&s.h_status, sizeof(IterStatus)));
+    RET_IF(dalloc(&s.d_ragoff, (size_t)h->J));
+    return MIXDIR_B200_OK;
+  };
+  const int st = body();
+  if (st != MIXDIR_B200_OK) {
+    std::string keep = g_err;
+    mixdir_b200_destroy(v);
+    g_err = keep;
+    return st;
+  }
+  *out = v;
+  return MIXDIR_B200_OK;
+}
+
+// concurrent fits of one batch: small fits are bound by launch latency and the dependent chain of
+// short kernels (tens of microseconds per iteration on a handful of SMs), so several of them share
+// the GPU without slowing each other; a fit whose row pass fills the GPU gains nothing
+static int batch_streams(const mixdir_b200_handle* h, int n_fits) {
+  int c = (int)std::min<int64_t>(8, std::max<int64_t>(1, ((int64_t)1 << 21) / std::max<int64_t>(h->n_rows, 1)));
+  if (const char* e = getenv("MIXDIR_B200_BATCH_STREAMS")) {
+    const int t = atoi(e);
+    if (t >= 1) c = std::min(t, 32);
+  }
+  if (needs_allreduce(h)) c = 1;  // collectives on one communicator must stay in one order
+  return std::max(1, std::min(c, n_fits));
+}
+
+extern "C" int mixdir_b200_fit_batch(mixdir_b200_handle* h, const mixdir_b200_fit_params* p, int n_fits,
+                                     const double* colsum_init, const double* phi_init,
+                                     double* elbo_trace, int* n_iter, int* converged, double* elbo,
+                                     double* lambda, double* prior_param, double* phi,
+                                     double* category_prob, int* warn_flags, int* status,
+                                     int* best, double* class_prob, int32_t* pred_class) {
+  RET_IF(check_fit_args(h, p));
+  if (n_fits < 1) return fail(MIXDIR_B200_BAD_ARGUMENT, "n_fits must be >= 1");
+  if (!colsum_init || !phi_init) return fail(MIXDIR_B200_BAD_ARGUMENT, "colsum_init / phi_init is NULL");
+  if (!elbo || !lambda || !category_prob)
+    return fail(MIXDIR_B200_BAD_ARGUMENT, "elbo, lambda and category_prob are needed to select the best fit");
+  DeviceGuard guard;
+  const int K = p->n_latent;
+  const size_t rag = (size_t)h->sum_ncat * K;
+  const size_t nprior = (size_t)(p->dp ? 2 : 1) * K;
+  const int C = batch_streams(h, n_fits);
+  if (C > 1) {
+    RET_IF(resolve_scan(h));  // the views share a completed upload
+    while ((int)h->views.size() < C - 1) {
+      mixdir_b200_handle* v = nullptr;
+      RET_IF(make_view(h, &v));
+      h->views.push_back(v);
+    }
+    for (auto* v : h->views) {
+      v->engine_pref = h->engine_pref;
+      v->pairing = h->pairing;
+    }
+  }
+  std::vector<int> st(n_fits, MIXDIR_B200_OK);
+  std::vector<std::string> msg(n_fits);
+  std::vector<mixdir_b200_timing> tms(C);
+  auto worker = [&](int w) {
+    mixdir_b200_handle* hw = w == 0 ? h : h->views[w - 1];
+    double loop_ms = 0, em_ms = 0;
+    int iters = 0, eml = 0, tl = 0;
+    for (int i = w; i < n_fits; i += C) {
+      st[i] = mixdir_b200_fit(hw, p, colsum_init + (size_t)i * K, phi_init + (size_t)i * rag,
+                              elbo_trace ? elbo_trace + (size_t)i * std::max(p->max_iter, 1) : nullptr,
+                              n_iter ? n_iter + i : nullptr, converged ? converged + i : nullptr,
+                              elbo + i, lambda + (size_t)i * K,
+                              prior_param ? prior_param + (size_t)i * nprior : nullptr,
+                              phi ? phi + (size_t)i * rag : nullptr, category_prob + (size_t)i * rag,
+                              nullptr, nullptr, warn_flags ? warn_flags + i : nullptr);
+      if (st[i] != MIXDIR_B200_OK) msg[i] = g_err;
+      loop_ms += hw->timing.fit_loop_ms; em_ms += hw->timing.em_kernel_ms;
+      iters += hw->timing.iterations; eml += hw->timing.em_launches; tl += hw->timing.total_launches;
+    }
+    tms[w] = hw->timing;
+    tms[w].fit_loop_ms = loop_ms; tms[w].em_kernel_ms = em_ms;
+    tms[w].iterations = iters; tms[w].em_launches = eml; tms[w].total_launches = tl;
+  };
+  if (C == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 1; w < C; w++) pool.emplace_back(worker, w);
+    worker(0);
+    for (auto& t : pool) t.join();
+  }
+  // timing of the batch: the engine description of worker 0, sums over every fit of the batch
+  // (fit_loop_ms therefore counts concurrent loops once each, not the batch's elapsed time)
+  h->timing = tms[0];
+  for (int w = 1; w < C; w++) {
+    h->timing.fit_loop_ms += tms[w].fit_loop_ms; h->timing.em_kernel_ms += tms[w].em_kernel_ms;
+    h->timing.iterations += tms[w].iterations; h->timing.em_launches += tms[w].em_launches;
+    h->timing.total_launches += tms[w].total_launches;
+  }
+  if (status) std::copy(st.begin(), st.end(), status);
+  // an error in any repetition ends mixdir() (stop() inside mixdir_vi, R/mixdir.R:120-134)
+  for (int i = 0; i < n_fits; i++)
+    if (st[i] != MIXDIR_B200_OK) {
+      if (best) *best = -1;
+      return fail(st[i], msg[i]);
+    }
+  // `if (result$ELBO < result_tmp$ELBO) result <- result_tmp` (R/mixdir.R:129-133): first maximum
+  int b = 0;
+  for (int i = 1; i < n_fits; i++)
+    if (elbo[b] < elbo[i]) b = i;
+  if (best) *best = b;
+  if (class_prob || pred_class)  // the arithmetic of the final pass == predict_class (R/predict.R:88-103)
+    return mixdir_b200_predict(h, K, lambda + (size_t)b * K, category_prob + (size_t)b * rag, class_prob,
+                               pred_class);
   return MIXDIR_B200_OK;
 }
 

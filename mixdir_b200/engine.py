@@ -221,6 +221,63 @@ class Engine:
             out["omega"] = prior[:K].copy()
         return out
 
+    def fit_batch(self, n_latent, colsum_inits, phi_inits, dp=False, alpha=None, beta=None, max_iter=100,
+                  epsilon=1e-3, n_cat_bound=0, want_class_prob=True, want_pred_class=True):
+        """The `repetitions` loop of mixdir() (R/mixdir.R:120-134) in one call: one fit per row of
+        colsum_inits [R, K] / phi_inits [R, ragged], small fits run concurrently on the device.
+        -> (list of per-fit dicts, index of the kept fit); class_prob / pred_class are computed for
+        the kept fit only."""
+        K = int(n_latent)
+        a1, a2 = 1.0, 1.0
+        if alpha is not None:
+            al = np.atleast_1d(np.asarray(alpha, dtype=float))
+            if al.size >= 1:
+                a1 = float(al[0])
+                a2 = float(al[1]) if (dp and al.size == 2) else float(al[0])
+        b = 0.1 if beta is None else float(np.atleast_1d(beta)[0])
+        p = FitParams(K, 1 if dp else 0, a1, a2, b, int(max_iter), float(epsilon), int(n_cat_bound))
+        cs = np.ascontiguousarray(colsum_inits, dtype=np.float64)
+        ph = np.ascontiguousarray(phi_inits, dtype=np.float64)
+        nrag = self.ragged_size(K)
+        if cs.ndim != 2 or cs.shape[1] != K:
+            raise ValueError("colsum_inits must be [repetitions, n_latent]")
+        R = cs.shape[0]
+        if ph.shape != (R, nrag):
+            raise ValueError("phi_inits must be [repetitions, ragged size]")
+        mi = max(int(max_iter), 1)
+        trace = np.full((R, mi), np.nan)
+        n_iter = np.zeros(R, dtype=np.int32)
+        conv = np.zeros(R, dtype=np.int32)
+        warn = np.zeros(R, dtype=np.int32)
+        status = np.zeros(R, dtype=np.int32)
+        elbo = np.full(R, np.nan)
+        lam = np.zeros((R, K))
+        prior = np.zeros((R, (2 if dp else 1) * K))
+        phi = np.zeros((R, nrag))
+        U = np.zeros((R, nrag))
+        best = C.c_int(-1)
+        cp = np.zeros((self.n_rows, K), order="F") if want_class_prob else None
+        pc = np.zeros(self.n_rows, dtype=np.int32) if want_pred_class else None
+        st = _capi.lib().mixdir_b200_fit_batch(
+            self._h, C.byref(p), R, _ptr(cs), _ptr(ph), _ptr(trace), _ptr(n_iter), _ptr(conv), _ptr(elbo),
+            _ptr(lam), _ptr(prior), _ptr(phi), _ptr(U), _ptr(warn), _ptr(status), C.byref(best), _ptr(cp),
+            _ptr(pc))
+        _check(st, self.n_features)
+        outs = []
+        for i in range(R):
+            n = int(n_iter[i])
+            o = dict(converged=bool(conv[i]), convergence=trace[i, :n].copy(), ELBO=float(elbo[i]), n_iter=n,
+                     lambda_=lam[i].copy(), pred_class=None, class_prob=None, category_prob=U[i].copy(),
+                     phi=phi[i].copy(), warn_flags=int(warn[i]))
+            if dp:
+                o["kappa1"], o["kappa2"] = prior[i, :K].copy(), prior[i, K:].copy()
+            else:
+                o["omega"] = prior[i].copy()
+            outs.append(o)
+        outs[best.value]["pred_class"] = pc
+        outs[best.value]["class_prob"] = cp
+        return outs, int(best.value)
+
     def predict(self, n_latent, lambda_, category_prob, want_class_prob=True, want_pred_class=True):
         K = int(n_latent)
         lam = np.ascontiguousarray(lambda_, dtype=np.float64)

@@ -82,3 +82,24 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "libmixdir_oracle" not in txt and \
                     "import oracle" not in txt and "from oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_r_adapter_parses():
+    """r_adapter/mixdir_b200_rcpp.cpp (the Rcpp glue a maintainer adds to the reference,
+    INTEGRATION.md) type-checks against include/mixdir_b200.h and a stand-in for <Rcpp.h> that declares
+    the Rcpp signatures it uses (the image has no R): every C-ABI call in it matches the header."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "r_adapter", "mixdir_b200_rcpp.cpp")
+    p = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror",
+                        "-I", os.path.join(ROOT, "tests", "rcpp_stub"), "-I", os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    text = open(src).read()
+    for fn in ("mixdir_b200_create_from_r_matrix", "mixdir_b200_fit_batch", "mixdir_b200_predict",
+               "mixdir_b200_feature_divergence", "mixdir_b200_destroy"):
+        assert fn in text
+    assert text.count("[[Rcpp::export]]") == 5
