@@ -149,6 +149,10 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
 
   // zeta <- zeta[, order(-colSums(zeta))]  (R/mixdir_vi_dp.R:97): stable, descending; applied
   // to the REDUCED statistics
+  // (identity first: NaN class masses -- an underflowing pass -- have no order and must not leave
+  // perm[] entries unset)
+  for (int k = tid; k < K; k += nt) perm[k] = k;
+  __syncthreads();
   for (int k = tid; k < K; k += nt) {
     if (a.dp && a.mode == 1) {
       const double c = stat_value(a, tab + k);
@@ -158,8 +162,6 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
         rank += (cl > c) || (cl == c && l < k);
       }
       perm[rank] = k;
-    } else {
-      perm[k] = k;
     }
   }
   __syncthreads();

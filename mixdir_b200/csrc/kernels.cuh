@@ -25,6 +25,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fastexp.cuh"
+
 namespace mxd {
 
 namespace cg = cooperative_groups;

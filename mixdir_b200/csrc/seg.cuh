@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
 #pragma unroll
       for (int o = KC / 2; o > 0; o >>= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
       const double m = (double)mf;
-      const double e = (mf == -INFINITY) ? 0.0 : exp(l - m);
+      const double e = exp_nonpos(l - m);  // (-inf - -inf = NaN -> 0)
       double s = e;
 #pragma unroll
       for (int o = KC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       double stot = 0.0;
 #pragma unroll
       for (int p = 0; p < 8; p++)
-        if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp(v[p].x - M);
+        if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp_nonpos(v[p].x - M);
       const double mine = mine_p->x;
-      f_o = (mine == -INFINITY) ? 0.0 : exp(mine - M) / stot;
+      f_o = (mine == -INFINITY) ? 0.0 : exp_nonpos(mine - M) / stot;
       logs_o = log(stot);
       M_o = M;
       const bool valid = (int64_t)t * R + wrow0 + lane < a.n_rows;

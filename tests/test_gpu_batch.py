@@ -87,12 +87,12 @@ def test_batch_is_cheaper_than_sequential_fits(mushroom):
 
 def test_batch_error_and_large_or_sharded_handles():
     # an underflowing repetition ends the call with the reference's stop() (R/mixdir_vi.R:77-81)
-    ncat = np.full(1000, 2, dtype=np.int32)
-    codes = np.ones((40, 1000), dtype=np.uint8)
-    cs, ph = _inits([1, 2], 40, ncat, 3)
+    ncat = np.full(1000, 2, dtype=np.int32)  # test-mixdir.R:109-114: 50 x 1000 columns
+    codes, _ = synth.make_codes(1, 50, ncat, 2)
+    cs, ph = _inits([1, 2], 50, ncat, 2)
     with Engine(codes, ncat) as eng:
-        with pytest.raises(ZetaUnderflow):
-            eng.fit_batch(3, cs, ph, max_iter=3)
+        with pytest.raises(ZetaUnderflow, match="underflow in the calculation of zeta"):
+            eng.fit_batch(2, cs, ph, max_iter=5)
     # bad shapes
     with Engine(synth.TOY_DATA, [3, 3, 3]) as eng:
         with pytest.raises(ValueError):

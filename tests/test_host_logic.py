@@ -1,5 +1,7 @@
 """CPU tests of the host-side mirror of mixdir()'s input handling (R/mixdir.R:91-118,
 R/predict.R:64-84) and of the deterministic synthetic generators."""
+import os
+
 import numpy as np
 import pytest
 
@@ -73,3 +75,42 @@ def test_toy_data_matches_helper_r():
     assert (t[1] == 3).all() and (t[6] == 3).all()          # rows 2, 7 = CCC
     for i in (4, 5, 7, 8, 9):
         assert t[i].tolist() == [1, 2, 2]                   # rows 5,6,8,9,10 = ABB
+
+
+def test_fast_exp_accuracy(tmp_path):
+    """mixdir_b200/csrc/fastexp.cuh (the branch-free exp of the soft-max weights) compiled for the HOST
+    against libm/long double: < 1 ulp over the normal range, 0 below -708, for -inf and for NaN."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "fastexp.cuh"
+#include <cstdio>
+#include <random>
+int main() {
+  std::mt19937_64 g(7);
+  std::uniform_real_distribution<double> wide(-700.0, 0.01), near(-40.0, 0.001);
+  double worst = 0;
+  for (long i = 0; i < 4000000; i++) {
+    const double x = (i & 1) ? wide(g) : near(g);
+    const double a = mxd::exp_nonpos(x);
+    const long double ref = expl((long double)x);
+    const double ulp = std::ldexp(1.0, std::ilogb((double)ref) - 52);
+    const double err = std::fabs((double)((long double)a - ref)) / ulp;
+    if (err > worst) worst = err;
+  }
+  const bool edges = mxd::exp_nonpos(0.0) == 1.0 && mxd::exp_nonpos(-709.0) == 0.0 &&
+                     mxd::exp_nonpos(-INFINITY) == 0.0 && mxd::exp_nonpos(NAN) == 0.0 &&
+                     mxd::exp_nonpos(INFINITY) == 0.0 && mxd::exp_nonpos(-1e300) == 0.0;
+  std::printf("%.4f %d\n", worst, edges ? 1 : 0);
+}
+''')
+    exe = tmp_path / "t"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([gxx, "-O2", "-std=c++17", "-I", os.path.join(root, "mixdir_b200", "csrc"), "-o", str(exe), str(src)],
+                   check=True)
+    worst, edges = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert float(worst) < 1.0 and edges == "1"
