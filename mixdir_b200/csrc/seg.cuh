@@ -211,9 +211,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
   for (int i = threadIdx.x; i < 4 * U; i += blockDim.x) ro_s[i] = a.eoff_rot[i];
   for (int i = threadIdx.x; i < a.njobs[own]; i += blockDim.x) jobs_s[i] = a.jobs[a.job0[own] + i];
   __syncthreads();
-  for (int i = threadIdx.x; i < a.NR2 * KC; i += blockDim.x) {
-    const int g2 = i / KC, c = i - g2 * KC;
-    T_s[(size_t)__ldg(a.slot_of_row + g2) * KC + c] = a.T2[(size_t)g2 * KP + rank * KC + c];
+  {  // table slice of this CTA: eight independent global loads in flight per thread
+    const int n = a.NR2 * KC, step = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * step) {
+      double v[8];
+      int sl[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + u * step;
+        if (i < n) {
+          const int g2 = i / KC, c = i - g2 * KC;
+          sl[u] = __ldg(a.slot_of_row + g2) * KC + c;
+          v[u] = __ldg(a.T2 + (size_t)g2 * KP + rank * KC + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (i0 + u * step < n) T_s[sl[u]] = v[u];
+    }
   }
   const double lp = a.logprior[kg];
   const bool kreal = kg < a.K;
@@ -417,10 +432,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
 
   // ---- flush: integer adds into the global statistics; last CTA writes the tail ----
   {
-    for (int i = threadIdx.x; i < a.SC[own] * SW; i += blockDim.x) {
-      const int r = i / SW, c = i - r * SW;
-      const unsigned long long v = S_s[i];
-      if (v) atomicAdd(&a.stats[(size_t)__ldg(a.srow_to_stat + a.sc0[own] + r) * KP + (FS ? 0 : rank * KC) + c], v);
+    {  // (the row map is read in batches of eight: one global-load latency per batch, not per entry)
+      const int n = a.SC[own] * SW, step = blockDim.x;
+      const int* map = a.srow_to_stat + a.sc0[own];
+      for (int i0 = threadIdx.x; i0 < n; i0 += 8 * step) {
+        int gr[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * step;
+          gr[u] = i < n ? __ldg(map + i / SW) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * step;
+          if (i < n) {
+            const unsigned long long v = S_s[i];
+            if (v) atomicAdd(&a.stats[(size_t)gr[u] * KP + (FS ? 0 : rank * KC) + i % SW], v);
+          }
+        }
+      }
     }
 #pragma unroll
     for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);

@@ -157,9 +157,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
   }
   for (int i = threadIdx.x; i < 4 * U; i += blockDim.x) ro_s[i] = a.eoff_rot[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < a.NR2 * KC; i += blockDim.x) {
-    const int g2 = i / KC, c = i - g2 * KC;
-    T_s[(size_t)__ldg(a.slot_of_row + g2) * KC + c] = a.T2[(size_t)g2 * KP + rank * KC + c];
+  {  // table slice of this CTA: eight independent global loads in flight per thread
+    const int n = a.NR2 * KC, step = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * step) {
+      double v[8];
+      int sl[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + u * step;
+        if (i < n) {
+          const int g2 = i / KC, c = i - g2 * KC;
+          sl[u] = __ldg(a.slot_of_row + g2) * KC + c;
+          v[u] = __ldg(a.T2 + (size_t)g2 * KP + rank * KC + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (i0 + u * step < n) T_s[sl[u]] = v[u];
+    }
   }
   const double lp = a.logprior[kg];
   const bool kreal = kg < a.K;
