@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MIXDIR_B200_ABI_VERSION 1
+#define MIXDIR_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define MIXDIR_B200_OK 0
@@ -233,6 +233,9 @@ typedef struct mixdir_b200_timing {
   int unit_elements;    /* fused: gather/scatter elements per row (features, pairs, padding) */
   int unit_pairs;       /* fused: features combined two-by-two into one element */
   int unit_table_rows;  /* fused: rows of the unit tables (sum over elements of their codes) */
+  int final_pass_engine;        /* last final pass / predict: 6 unit kernel (k_predict_units), 7 feature
+                                   table in shared memory (k_predict_smem), 8 general kernel; 0 none */
+  double final_pass_kernel_ms;  /* its CUDA-event time on device 0: table build + the pass, no copies */
 } mixdir_b200_timing;
 
 /* Inner loop of find_defining_features() (/root/reference/R/predict.R:266-339; the `vapply` over the

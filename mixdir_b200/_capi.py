@@ -41,7 +41,8 @@ class Timing(C.Structure):
                 ("iterations", C.c_int), ("em_launches", C.c_int), ("total_launches", C.c_int),
                 ("engine", C.c_int), ("classes_per_cta", C.c_int), ("cluster_size", C.c_int),
                 ("grid_ctas", C.c_int), ("smem_bytes", C.c_int), ("unit_elements", C.c_int),
-                ("unit_pairs", C.c_int), ("unit_table_rows", C.c_int)]
+                ("unit_pairs", C.c_int), ("unit_table_rows", C.c_int),
+                ("final_pass_engine", C.c_int), ("final_pass_kernel_ms", C.c_double)]
 
 
 _lib = None

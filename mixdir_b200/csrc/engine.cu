@@ -29,6 +29,7 @@
 #include "seg.cuh"
 #include "iter.cuh"
 #include "predict.cuh"
+#include "predict_units.cuh"
 #include "features.cuh"
 
 using namespace mxd;
@@ -178,6 +179,15 @@ struct Plan {
   SegPlan sp;
 };
 
+// final pass / predict over units (predict_units.cuh): its own pair plan and packed codes --
+// no statistics table competes for shared memory here, so more classes fit one CTA than in the fit
+struct PredPlan {
+  bool valid = false;
+  int K = 0, KC = 0, P = 1, W = 16, R = 256;
+  size_t smem = 0;
+  UnitPlan up;
+};
+
 struct Shard {
   int device = 0;
   bool view = false;  // shares the uploaded data of another handle's shard (mixdir_b200_fit_batch)
@@ -222,6 +232,17 @@ struct Shard {
   int64_t seg_tiles = 0;           // tiles of d_seg already built
   double* d_T2 = nullptr;          // [NR2][KP] (workspace)
   int ws_NR2 = 0;
+  // predict over units: plan signature + device copies, kept while the plan stays the same
+  std::vector<UnitDesc> pred_sig;
+  bool pred_valid = false;
+  UnitDesc* d_pdesc = nullptr;
+  int2* d_pt2src = nullptr;
+  int* d_pslot = nullptr;
+  int* d_peoff = nullptr;
+  uint8_t* d_pcodes = nullptr;
+  double* d_pT2 = nullptr;
+  size_t pT2_cap = 0;
+  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
   PriorState* d_prior = nullptr;
   IterStatus* d_status = nullptr;
   IterStatus* h_status = nullptr;  // pinned + mapped: k_iter writes it, the host polls it
@@ -437,6 +458,12 @@ static void free_shard(Shard& s) {
   dfree(s.d_slot); dfree(s.d_eoff); dfree(s.d_elem); dfree(s.d_erange);
   dfree(s.d_seg); dfree(s.d_jobs); dfree(s.d_srow2stat);
   s.unit_valid = false;
+  dfree(s.d_pdesc); dfree(s.d_pt2src); dfree(s.d_pslot); dfree(s.d_peoff); dfree(s.d_pcodes); dfree(s.d_pT2);
+  s.pred_valid = false;
+  s.pT2_cap = 0;
+  if (s.ev_p0) cudaEventDestroy(s.ev_p0);
+  if (s.ev_p1) cudaEventDestroy(s.ev_p1);
+  s.ev_p0 = s.ev_p1 = nullptr;
   if (s.copy_stream) {
     cudaStreamSynchronize(s.copy_stream);  // an upload may still be in flight
     cudaStreamDestroy(s.copy_stream);
@@ -2369,8 +2396,172 @@ extern "C" int mixdir_b200_fit_batch(mixdir_b200_handle* h, const mixdir_b200_fi
   return MIXDIR_B200_OK;
 }
 
-// final pass on every shard with the tables already in d_logU / d_lambda_pad
+// ---------------------------------------------------------------------------
+// large results to (pageable) host memory: device -> page-locked staging in 64 MB pieces, each piece
+// copied out by a few host threads while the next one crosses PCIe.  (cudaMemcpy to pageable memory
+// bounces through the driver at 3-4 GB/s: 0.68 s for the 2.56 GB class_prob of 10M x 32.)
+// Copies `height` runs of `width` bytes; the runs are dst_pitch / src_pitch bytes apart.
+// ---------------------------------------------------------------------------
+static void host_copy_parallel(unsigned char* dst, const unsigned char* src, size_t bytes, int T) {
+  if (bytes < ((size_t)4 << 20) || T <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
+  for (int t = 0; t < T; t++) {
+    const size_t o = (size_t)t * per;
+    if (o >= bytes) break;
+    pool.emplace_back([=]() { memcpy(dst + o, src + o, std::min(per, bytes - o)); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+static int d2h_bulk(Shard& s, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width,
+                    size_t height) {
+  const size_t total = width * height;
+  if (total == 0) return MIXDIR_B200_OK;
+  if (total < ((size_t)8 << 20)) {
+    CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, height, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    return MIXDIR_B200_OK;
+  }
+  const size_t kPiece = (size_t)64 << 20;
+  // pieces: whole runs when a run is smaller than a piece, else slices of one run
+  struct Piece { size_t run, off, len, nruns; };
+  std::vector<Piece> pieces;
+  if (width >= kPiece) {
+    for (size_t r = 0; r < height; r++)
+      for (size_t o = 0; o < width; o += kPiece) pieces.push_back({r, o, std::min(kPiece, width - o), 1});
+  } else {
+    const size_t per = std::max<size_t>(1, kPiece / width);
+    for (size_t r = 0; r < height; r += per) pieces.push_back({r, 0, width, std::min(per, height - r)});
+  }
+  unsigned char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  const int T = std::min(host_pack_threads(), 8);
+  auto body = [&]() -> int {
+    for (int b = 0; b < 2; b++) {
+      CU_TRY(cache::pin_get((void**)&stage[b], kPiece));
+      CU_TRY(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+    }
+    auto issue = [&](size_t i) -> int {
+      const Piece& p = pieces[i];
+      const unsigned char* sp = (const unsigned char*)src + p.run * src_pitch + p.off;
+      if (p.nruns == 1)
+        CU_TRY(cudaMemcpyAsync(stage[i & 1], sp, p.len, cudaMemcpyDeviceToHost, s.stream));
+      else
+        CU_TRY(cudaMemcpy2DAsync(stage[i & 1], width, sp, src_pitch, width, p.nruns, cudaMemcpyDeviceToHost, s.stream));
+      CU_TRY(cudaEventRecord(ev[i & 1], s.stream));
+      return MIXDIR_B200_OK;
+    };
+    RET_IF(issue(0));
+    for (size_t i = 0; i < pieces.size(); i++) {
+      if (i + 1 < pieces.size()) RET_IF(issue(i + 1));  // its buffer was emptied in the previous round
+      CU_TRY(cudaEventSynchronize(ev[i & 1]));
+      const Piece& p = pieces[i];
+      unsigned char* dp = (unsigned char*)dst + p.run * dst_pitch + p.off;
+      if (p.nruns == 1 || dst_pitch == width) {
+        host_copy_parallel(dp, stage[i & 1], p.len * p.nruns, T);
+      } else {
+        for (size_t r = 0; r < p.nruns; r++) host_copy_parallel(dp + r * dst_pitch, stage[i & 1] + r * width, width, T);
+      }
+    }
+    return MIXDIR_B200_OK;
+  };
+  const int st = body();
+  if (st != MIXDIR_B200_OK) cudaStreamSynchronize(s.stream);
+  for (int b = 0; b < 2; b++) {
+    if (ev[b]) cudaEventDestroy(ev[b]);
+    if (stage[b]) cache::pin_put(stage[b]);
+  }
+  return st;
+}
+
+// ---------------------------------------------------------------------------
+// final pass / predict
+// ---------------------------------------------------------------------------
+typedef void (*predu_fn)(PredictUnitArgs);
+static predu_fn pick_predict_units(int KC) {
+  return KC == 8 ? k_predict_units<8> : (KC == 16 ? k_predict_units<16> : k_predict_units<32>);
+}
+
+// unit plan of the predict kernel for K classes: as many feature pairs as shared memory allows next
+// to the tile buffers; classes per CTA and cluster size by a cost in shared-memory wavefronts per row
+static bool plan_predict(const mixdir_b200_handle* h, const Shard& s, int K, PredPlan* out) {
+  if (h->CB != 1 || getenv("MIXDIR_B200_OLD_PREDICT")) return false;
+  const uint8_t* na = (h->scan_resolved && (int)h->has_na.size() == h->J) ? h->has_na.data() : nullptr;
+  PredPlan best;
+  double best_cost = 1e300;
+  const int kcs[3] = {32, 16, 8};
+  for (int KC : kcs) {
+    if (KC > 8 && K <= KC / 2) continue;  // a narrower slice holds all classes
+    const int P = (K + KC - 1) / KC;
+    if (P > 8) continue;
+    PredPlan c;
+    c.K = K; c.KC = KC; c.P = P; c.W = 16; c.R = 256;
+    bool found = false;
+    const int m_hi = h->pairing ? h->J / 2 : 0;
+    const int w_lo = (h->J - m_hi + 3) / 4, w_hi = (h->J + 3) / 4;
+    for (int w = w_lo; w <= w_hi && !found; w++) {
+      const int m = std::max(0, h->J - 4 * w);
+      if (m > m_hi || !make_units(h, m, &c.up, true, na)) continue;
+      layout_units(&c.up, KC);
+      c.smem = PredictUnitSmem(c.up.srows, KC, c.R, c.up.WPRu, P).total;
+      found = c.smem <= (size_t)s.smem_optin;
+    }
+    if (!found) continue;
+    const int n_clusters = s.sm_count / P;
+    const double used = (double)n_clusters * P / s.sm_count;
+    const double cost = P * (c.up.U * (KC / 16.0) + (KC == 8 ? 40.0 : 60.0)) / used;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+      best.valid = true;
+    }
+  }
+  if (!best.valid) return false;
+  *out = best;
+  return true;
+}
+
+// device copies of the predict plan + the packed codes of this shard (kept while the plan is the same)
+static int ensure_predict_units(mixdir_b200_handle* h, Shard& s, const PredPlan& pp) {
+  const UnitPlan& up = pp.up;
+  std::vector<UnitDesc> sig = up.desc;
+  sig.push_back(UnitDesc{pp.KC, up.Q, up.srows, pp.R});
+  if (s.pred_valid && s.pred_sig.size() == sig.size() &&
+      memcmp(s.pred_sig.data(), sig.data(), sig.size() * sizeof(UnitDesc)) == 0)
+    return MIXDIR_B200_OK;
+  s.pred_valid = false;
+  CU_TRY(cudaStreamSynchronize(s.stream));  // the staging area is reused below
+  dfree(s.d_pdesc); dfree(s.d_pt2src); dfree(s.d_pslot); dfree(s.d_peoff); dfree(s.d_pcodes);
+  RET_IF(pin_reset(s, unit_stage_bytes(up) + 4096));
+  RET_IF(send_vec(s, &s.d_pdesc, up.desc));
+  RET_IF(send_vec(s, &s.d_pt2src, up.t2src));
+  RET_IF(send_vec(s, &s.d_pslot, up.slot));
+  RET_IF(send_vec(s, &s.d_peoff, up.eoff_rot));
+  const size_t rowb = (size_t)up.WPRu * 4;
+  const int64_t R = pp.R, rows_alloc = (s.n_rows + R - 1) / R * R + kRowPad;
+  RET_IF(dalloc(&s.d_pcodes, (size_t)rows_alloc * rowb));
+  const int64_t full = s.n_rows / R * R;
+  CU_TRY(cudaMemsetAsync(s.d_pcodes + (size_t)full * rowb, 0, (size_t)(rows_alloc - full) * rowb, s.stream));
+  if (s.n_rows > 0) {
+    const int grid = (int)std::min<int64_t>((int64_t)s.sm_count * 16, (s.n_rows * up.WPRu + 255) / 256);
+    k_pack_units<<<grid, 256, 0, s.stream>>>(s.d_codes, h->row_bytes, s.n_rows, s.d_pdesc, up.WPRu, pp.R,
+                                             reinterpret_cast<uint32_t*>(s.d_pcodes));
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaStreamSynchronize(s.stream));  // the staged arrays have been read
+  s.pred_sig = sig;
+  s.pred_valid = true;
+  return MIXDIR_B200_OK;
+}
+
+// final pass on every shard with the tables already in d_logU (row stride KP) / d_lambda_pad
 static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob, int32_t* pred_class) {
+  h->timing.final_pass_kernel_ms = 0;
+  h->timing.final_pass_engine = 0;
   for (auto& s : h->shards) {
     if (s.n_rows == 0) continue;
     CU_TRY(cudaSetDevice(s.device));
@@ -2378,58 +2569,121 @@ static int run_predict(mixdir_b200_handle* h, int K, int KP, double* class_prob,
     int32_t* d_pc = nullptr;
     if (class_prob) RET_IF(dalloc(&d_cp, (size_t)s.n_rows * K));
     if (pred_class) RET_IF(dalloc(&d_pc, (size_t)s.n_rows));
-    // shared-memory table kernel when K <= 32 and the table fits, else the general kernel
-    const int KC = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
-    const int FPW = 4 / h->CB, W = 16, RPW = 32 / KC;
-    const PredictSmem L(h->NR, KC, W, 8, h->WPR, FPW);
-    typedef void (*pfn)(PredictSmemArgs);
-    pfn fn = nullptr;
-    if (K <= 32 && RPW <= FPW * 8 && L.total <= (size_t)s.smem_optin) {
-      if (h->CB == 1) fn = KC == 8 ? k_predict_smem<8, 1> : (KC == 16 ? k_predict_smem<16, 1> : k_predict_smem<32, 1>);
-      else fn = KC == 8 ? k_predict_smem<8, 2> : (KC == 16 ? k_predict_smem<16, 2> : k_predict_smem<32, 2>);
-      if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)L.total) != cudaSuccess) {
-        cudaGetLastError();
-        fn = nullptr;
-      }
+    if (!s.ev_p0) {
+      CU_TRY(cudaEventCreate(&s.ev_p0));
+      CU_TRY(cudaEventCreate(&s.ev_p1));
     }
-    if (fn) {
-      const int R = W * 8 * RPW;
-      PredictSmemArgs a;
-      a.codes = reinterpret_cast<const uint32_t*>(s.d_codes);
+    int engine = 0;
+    PredPlan pp;
+    if (plan_predict(h, s, K, &pp)) {  // packed unit codes + pair table of log U in shared memory
+      RET_IF(ensure_predict_units(h, s, pp));
+      const size_t tab2 = (size_t)pp.up.NR2 * KP;
+      if (s.pT2_cap < tab2) {
+        dfree(s.d_pT2);
+        RET_IF(dalloc(&s.d_pT2, tab2));
+        s.pT2_cap = tab2;
+      }
+      predu_fn fn = pick_predict_units(pp.KC);
+      CU_TRY(ensure_smem_attr(s, (const void*)fn, pp.smem));
+      CU_TRY(cudaEventRecord(s.ev_p0, s.stream));
+      const int g2 = (int)std::min<size_t>((tab2 + 255) / 256, (size_t)s.sm_count * 4);
+      k_build_T2<<<g2, 256, 0, s.stream>>>(s.d_pt2src, pp.up.NR2, KP, s.d_logU, s.d_pT2);
+      CU_TRY(cudaGetLastError());
+      PredictUnitArgs a;
+      a.codes = reinterpret_cast<const uint32_t*>(s.d_pcodes);
       a.n_rows = s.n_rows;
-      a.n_tiles = (int)((s.n_rows + R - 1) / R);
-      a.WPR = h->WPR;
-      a.NR = h->NR;
+      a.n_tiles = (int)((s.n_rows + pp.R - 1) / pp.R);
+      a.R = pp.R;
+      a.WPR = pp.up.WPRu;
+      a.NR2 = pp.up.NR2;
+      a.srows = pp.up.srows;
       a.K = K;
       a.KP = KP;
-      a.rowoff_pad = s.d_rowoff_pad;
-      a.logU = s.d_logU;
+      a.P = pp.P;
+      a.eoff_rot = s.d_peoff;
+      a.slot_of_row = s.d_pslot;
+      a.T2 = s.d_pT2;
       a.lambda = s.d_lambda_pad;
       a.class_prob = d_cp;
       a.pred_class = d_pc;
-      const int grid = std::min(s.sm_count, a.n_tiles);
-      fn<<<grid, 32 * W, L.total, s.stream>>>(a);
+      const int nclus = std::max(1, std::min(s.sm_count / pp.P, a.n_tiles));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nclus * pp.P);
+      cfg.blockDim = dim3(32 * pp.W);
+      cfg.dynamicSmemBytes = pp.smem;
+      cfg.stream = s.stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = pp.P;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      CU_TRY(cudaLaunchKernelEx(&cfg, fn, a));
+      engine = 6;
     } else {
-      PredictArgs a = {s.d_codes, h->row_bytes, s.n_rows, h->J, K, KP, s.d_rowoff, s.d_logU,
-                       s.d_lambda_pad, d_cp, d_pc};
-      const int grid = s.sm_count * 8;
-      if (h->CB == 1)
-        k_predict<1><<<grid, 256, 0, s.stream>>>(a);
-      else
-        k_predict<2><<<grid, 256, 0, s.stream>>>(a);
+      // 2-byte codes: log-U table in shared memory when K <= 32 and it fits, else the general kernel
+      const int KC = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+      const int FPW = 4 / h->CB, W = 16, RPW = 32 / KC;
+      const PredictSmem L(h->NR, KC, W, 8, h->WPR, FPW);
+      typedef void (*pfn)(PredictSmemArgs);
+      pfn fn = nullptr;
+      if (K <= 32 && RPW <= FPW * 8 && L.total <= (size_t)s.smem_optin) {
+        if (h->CB == 1) fn = KC == 8 ? k_predict_smem<8, 1> : (KC == 16 ? k_predict_smem<16, 1> : k_predict_smem<32, 1>);
+        else fn = KC == 8 ? k_predict_smem<8, 2> : (KC == 16 ? k_predict_smem<16, 2> : k_predict_smem<32, 2>);
+        if (ensure_smem_attr(s, (const void*)fn, L.total) != cudaSuccess) {
+          cudaGetLastError();
+          fn = nullptr;
+        }
+      }
+      CU_TRY(cudaEventRecord(s.ev_p0, s.stream));
+      if (fn) {
+        const int R = W * 8 * RPW;
+        PredictSmemArgs a;
+        a.codes = reinterpret_cast<const uint32_t*>(s.d_codes);
+        a.n_rows = s.n_rows;
+        a.n_tiles = (int)((s.n_rows + R - 1) / R);
+        a.WPR = h->WPR;
+        a.NR = h->NR;
+        a.K = K;
+        a.KP = KP;
+        a.rowoff_pad = s.d_rowoff_pad;
+        a.logU = s.d_logU;
+        a.lambda = s.d_lambda_pad;
+        a.class_prob = d_cp;
+        a.pred_class = d_pc;
+        const int grid = std::min(s.sm_count, a.n_tiles);
+        fn<<<grid, 32 * W, L.total, s.stream>>>(a);
+        engine = 7;
+      } else {
+        PredictArgs a = {s.d_codes, h->row_bytes, s.n_rows, h->J, K, KP, s.d_rowoff, s.d_logU,
+                         s.d_lambda_pad, d_cp, d_pc};
+        const int grid = s.sm_count * 8;
+        if (h->CB == 1)
+          k_predict<1><<<grid, 256, 0, s.stream>>>(a);
+        else
+          k_predict<2><<<grid, 256, 0, s.stream>>>(a);
+        engine = 8;
+      }
     }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(s.ev_p1, s.stream));
+    int st = MIXDIR_B200_OK;
     if (class_prob)  // shard block of an n_rows x K column-major matrix
-      CU_TRY(cudaMemcpy2DAsync(class_prob + s.row0, (size_t)h->n_rows * sizeof(double), d_cp,
-                               (size_t)s.n_rows * sizeof(double), (size_t)s.n_rows * sizeof(double),
-                               K, cudaMemcpyDeviceToHost, s.stream));
-    if (pred_class)
-      CU_TRY(cudaMemcpyAsync(pred_class + s.row0, d_pc, (size_t)s.n_rows * sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, s.stream));
-    CU_TRY(cudaStreamSynchronize(s.stream));
+      st = d2h_bulk(s, class_prob + s.row0, (size_t)h->n_rows * sizeof(double), d_cp,
+                    (size_t)s.n_rows * sizeof(double), (size_t)s.n_rows * sizeof(double), (size_t)K);
+    if (st == MIXDIR_B200_OK && pred_class)
+      st = d2h_bulk(s, pred_class + s.row0, 0, d_pc, 0, (size_t)s.n_rows * sizeof(int32_t), 1);
+    if (st == MIXDIR_B200_OK && cudaStreamSynchronize(s.stream) != cudaSuccess) st = fail(MIXDIR_B200_CUDA_ERROR, "final pass failed");
     dfree(d_cp);
     dfree(d_pc);
+    RET_IF(st);
+    if (&s == &h->shards[0]) {
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, s.ev_p0, s.ev_p1));
+      h->timing.final_pass_kernel_ms = ms;
+      h->timing.final_pass_engine = engine;
+    }
   }
   return MIXDIR_B200_OK;
 }

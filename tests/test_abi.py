@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_capi.SYMBOLS) == names
-    assert L.mixdir_b200_abi_version() == 1
+    assert L.mixdir_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
