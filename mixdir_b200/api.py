@@ -131,10 +131,9 @@ def _recode_new(obj, newdata):
     """name matching, unseen-level warning and NA handling of predict_class (R/predict.R:64-84)."""
     names, categories = obj["_names"], obj["_categories"]
     nd_names, nd_cols = _as_columns(newdata)
+    # columns the model does not know are ignored: predict_class rebuilds X from names(categories)
+    # only (R/predict.R:64-86), which makes its later stop() for unknown columns (:95-96) unreachable
     by_name = dict(zip(nd_names, nd_cols))
-    for n in nd_names:
-        if n not in names:  # stop() of R/predict.R:95-96
-            raise ValueError(f"The new observation X contains a category {n} not in the data")
     codes, unseen = recode_for_predict(by_name, names, categories, obj.get("na_handle") or "ignore")
     for col, vals in unseen.items():  # warning() of R/predict.R:75-80
         lst = ",".join(f'"{v}"' for v in sorted(vals))

@@ -62,63 +62,79 @@ __device__ __forceinline__ double stat_value(const IterArgs& a, size_t i) {
 
 // omega / kappa, prior logits and the ELBO terms A and E from the class masses cs[K].
 // Called by all threads of one block; red: >= 6*kMaxClasses doubles of shared memory.
+// The special functions of a class (digamma / lgamma of omega, or of kappa1, kappa2 and their sum)
+// are independent: they are dealt to different threads, so their serial latencies overlap.
 __device__ void prior_step(const IterArgs& a, const double* cs, double* red) {
-  const int K = a.K;
+  const int K = a.K, nt = blockDim.x, tid = threadIdx.x;
   PriorState* st = a.st;
   double *lg1 = red, *lg2 = red + kMaxClasses, *lg12 = red + 2 * kMaxClasses,
          *d1 = red + 3 * kMaxClasses, *d2 = red + 4 * kMaxClasses, *d12 = red + 5 * kMaxClasses;
+  __shared__ double om_s[kMaxClasses], k2_s[kMaxClasses], tot_s[2];
   if (!a.dp) {
     // omega <- alpha + colSums(zeta)   (R/mixdir_vi.R:61)
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const double om = a.a1 + cs[k];
-      st->omega[k] = om;
-      d1[k] = dev_digamma(om);
-      lg1[k] = lgamma(om);
+    for (int k = tid; k < K; k += nt) om_s[k] = a.a1 + cs[k];
+    __syncthreads();
+    for (int i = tid; i < 2 * K + 2; i += nt) {
+      if (i < K) {
+        d1[i] = dev_digamma(om_s[i]);
+      } else if (i < 2 * K) {
+        lg1[i - K] = lgamma(om_s[i - K]);
+      } else {  // digamma / lgamma of sum(omega): mixdir_impl.cpp:59, R/mixdir_vi.R:177-179
+        double so = 0;
+        for (int k = 0; k < K; k++) so += om_s[k];
+        tot_s[i - 2 * K] = (i == 2 * K) ? dev_digamma(so) : lgamma(so);
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double so = 0;
-      for (int k = 0; k < K; k++) so += st->omega[k];
-      const double dso = dev_digamma(so);  // mixdir_impl.cpp:59
+    for (int k = tid; k < K; k += nt) {
+      const double e = d1[k] - tot_s[0];
+      st->omega[k] = om_s[k];
+      st->e1[k] = e;
+      a.logprior[k] = e;
+      d2[k] = e;
+    }
+    for (int k = K + tid; k < a.KP; k += nt) a.logprior[k] = -INFINITY;
+    __syncthreads();
+    if (tid == 0) {
       double sA = 0, sl = 0, sE = 0;
       for (int k = 0; k < K; k++) {
-        const double e = d1[k] - dso;
-        st->e1[k] = e;
-        a.logprior[k] = e;
-        sA += (a.a1 - 1.0) * e;
+        sA += (a.a1 - 1.0) * d2[k];
         sl += lg1[k];
-        sE += (st->omega[k] - 1.0) * e;
+        sE += (om_s[k] - 1.0) * d2[k];
       }
-      for (int k = K; k < a.KP; k++) a.logprior[k] = -INFINITY;
-      st->termA = a.termA_const + sA;                         // R/mixdir_vi.R:164-166
-      st->termE = -lgamma(so) + sl - sE;                      // R/mixdir_vi.R:177-179
+      st->termA = a.termA_const + sA;   // R/mixdir_vi.R:164-166
+      st->termE = -tot_s[1] + sl - sE;  // R/mixdir_vi.R:177-179
     }
   } else {
     // kappa1 <- a1 + colSums(zeta); kappa2_k <- a2 + sum_{l>k} colSums(zeta)_l  (dp.R:68-71)
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       double tail = 0;
       for (int k = K - 1; k >= 0; k--) {
-        st->kappa2[k] = a.a2 + tail;
+        k2_s[k] = a.a2 + tail;
         tail += cs[k];
       }
     }
+    for (int k = tid; k < K; k += nt) om_s[k] = a.a1 + cs[k];
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const double k1 = a.a1 + cs[k];
-      const double k2 = st->kappa2[k];
-      st->omega[k] = k1;
-      d1[k] = dev_digamma(k1);
-      d2[k] = dev_digamma(k2);
-      d12[k] = dev_digamma(k1 + k2);
-      lg1[k] = lgamma(k1);
-      lg2[k] = lgamma(k2);
-      lg12[k] = lgamma(k1 + k2);
+    for (int i = tid; i < 6 * K; i += nt) {
+      const int k = i % K, what = i / K;
+      const double k1 = om_s[k], k2 = k2_s[k];
+      if (what == 0) d1[k] = dev_digamma(k1);
+      else if (what == 1) d2[k] = dev_digamma(k2);
+      else if (what == 2) d12[k] = dev_digamma(k1 + k2);
+      else if (what == 3) lg1[k] = lgamma(k1);
+      else if (what == 4) lg2[k] = lgamma(k2);
+      else lg12[k] = lgamma(k1 + k2);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    for (int k = tid; k < K; k += nt) {
+      st->omega[k] = om_s[k];
+      st->kappa2[k] = k2_s[k];
+    }
+    if (tid == 0) {
       double skp = 0, sA = 0, sE = 0;
       for (int k = 0; k < K; k++) {
-        const double k1 = st->omega[k], k2 = st->kappa2[k];
+        const double k1 = om_s[k], k2 = k2_s[k];
         const double e1 = d1[k] - d12[k];
         const double e2 = d2[k] - d12[k];
         st->e1[k] = e1;
@@ -138,10 +154,13 @@ __device__ void prior_step(const IterArgs& a, const double* cs, double* red) {
 }
 
 constexpr int kIterThreads = 256;
+constexpr int kIterCells = 1792;  // (class, category) cells of an element kept in shared memory
 
 __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
   __shared__ int perm[kMaxClasses];
   __shared__ double red[6 * kMaxClasses];  // [3][256] reductions; digamma sums; prior scratch
+  __shared__ double ph_s[kIterCells];      // phi of the element's cells, then their table values T
+  __shared__ double dg_s[kIterCells];      // digamma(phi)
   __shared__ int is_last;
   if (a.mode == 1 && a.status->stop) return;  // uniform over the grid (set by an earlier launch)
   const int K = a.K, KP = a.KP, nt = blockDim.x, tid = threadIdx.x;
@@ -153,73 +172,133 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
   // perm[] entries unset)
   for (int k = tid; k < K; k += nt) perm[k] = k;
   __syncthreads();
-  for (int k = tid; k < K; k += nt) {
-    if (a.dp && a.mode == 1) {
-      const double c = stat_value(a, tab + k);
+  if (a.dp && a.mode == 1) {
+    for (int k = tid; k < K; k += nt) red[k] = stat_value(a, tab + k);
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+      const double c = red[k];
       int rank = 0;
       for (int l = 0; l < K; l++) {
-        const double cl = stat_value(a, tab + l);
+        const double cl = red[l];
         rank += (cl > c) || (cl == c && l < k);
       }
       perm[rank] = k;
     }
+    __syncthreads();
+  }
+
+  // The element of this block: one feature, or the two features of a pair.  Its (class, category)
+  // cells are numbered i = r * K + k, feature a first.  Everything that needs a special function
+  // is an independent work item dealt to the threads (their latencies, ~1 us each at this
+  // occupancy, were paid one after the other before):
+  //   item [0, cells)          digamma(phi_cell)
+  //   item [cells, 2 cells)    lgamma(phi_cell)                 (entrop_phi, mode 1)
+  //   then 3 per (feature, k): digamma(sum_{r<n_cat} phi), digamma(sum_r phi), lgamma(sum_r phi)
+  const int2 el = a.elem[blockIdx.x];
+  const int ja = el.x, jb = el.y;
+  const int Ca = a.ncat[ja], Cb = jb >= 0 ? a.ncat[jb] : 0;
+  const size_t g0a = (size_t)a.rowoff[ja], g0b = jb >= 0 ? (size_t)a.rowoff[jb] : 0;
+  const int cellsA = K * Ca, cells = cellsA + K * Cb;
+  const bool in_smem = cells <= kIterCells;
+  const int nf = jb >= 0 ? 2 : 1;
+  double* dsb = red;                    // [2][K] digamma of the bounded sum (mixdir_impl.cpp:61-72)
+  double* dsa = red + 2 * kMaxClasses;  // [2][K] digamma of the full sum
+  double p0 = 0, p1 = 0, p2 = 0;        // this thread's share of the C, D, G terms
+
+  // phi[[j]][[k]][r] <- sum(zeta[,k] * (X[,j]==r), na.rm=TRUE) + beta  (R/mixdir_vi.R:88)
+  for (int i = tid; i < cells; i += nt) {
+    const bool fa = i < cellsA;
+    const int ii = fa ? i : i - cellsA;
+    const int r = ii / K, k = ii - r * K;
+    const size_t g = (fa ? g0a : g0b) + 1 + r;
+    double ph;
+    if (a.mode == 1) {
+      ph = stat_value(a, g * KP + perm[k]) + a.beta;
+      a.phi[g * KP + k] = ph;
+    } else {
+      ph = a.phi[g * KP + k];
+    }
+    if (in_smem) ph_s[i] = ph;
   }
   __syncthreads();
-
-  const int2 el = a.elem[blockIdx.x];
-  double p0 = 0, p1 = 0, p2 = 0;  // this thread's share of the C, D, G terms
-  double* ds_bound = red;                   // [K]
-  double* ds_all = red + kMaxClasses;       // [K]
-  for (int f = 0; f < 2; f++) {
-    const int j = f == 0 ? el.x : el.y;
-    if (j < 0) break;
-    const int C = a.ncat[j];
-    const size_t g0 = (size_t)a.rowoff[j];
-    const int cells = K * C;
-    // phi[[j]][[k]][r] <- sum(zeta[,k] * (X[,j]==r), na.rm=TRUE) + beta  (R/mixdir_vi.R:88)
-    if (a.mode == 1)
-      for (int i = tid; i < cells; i += nt) {
-        const int r = i / K, k = i - r * K;
-        a.phi[(g0 + 1 + r) * KP + k] = stat_value(a, (g0 + 1 + r) * KP + perm[k]) + a.beta;
+  const int items = 2 * cells + 3 * nf * K;
+  for (int v = tid; v < items; v += nt) {
+    if (v < 2 * cells) {
+      const int i = v < cells ? v : v - cells;
+      double ph;
+      if (in_smem) {
+        ph = ph_s[i];
+      } else {
+        const bool fa = i < cellsA;
+        const int ii = fa ? i : i - cellsA;
+        const int r = ii / K, k = ii - r * K;
+        ph = a.phi[((fa ? g0a : g0b) + 1 + r) * KP + k];
       }
-    __syncthreads();
-    for (int k = tid; k < K; k += nt) {
-      double sum_all = 0, sum_bound = 0;
-      for (int r = 0; r < C; r++) {
-        const double ph = a.phi[(g0 + 1 + r) * KP + k];
-        sum_all += ph;
-        if (r < a.n_cat_bound) sum_bound += ph;
+      if (v < cells) {
+        if (in_smem) dg_s[i] = dev_digamma(ph);  // (elements too large for shared memory compute it below)
+      } else if (a.mode == 1) {
+        p2 += lgamma(ph);  // entrop_phi, R/mixdir_vi.R:190-192
       }
-      ds_bound[k] = dev_digamma(sum_bound);  // mixdir_impl.cpp:61-72
-      ds_all[k] = dev_digamma(sum_all);      // R-level digamma(sum(phi_jk))
-      a.T[g0 * KP + k] = 0.0;                // NA row
-      if (a.mode == 1) p2 -= lgamma(sum_all);  // entrop_phi, R/mixdir_vi.R:190-192
-    }
-    __syncthreads();
-    for (int i = tid; i < cells; i += nt) {
-      const int r = i / K, k = i - r * K;
-      const size_t g = g0 + 1 + r;
-      const double ph = a.phi[g * KP + k];
-      const double dg = dev_digamma(ph);
-      const double t = dg - ds_bound[k];  // mixdir_impl.cpp:80
-      a.T[g * KP + k] = t;
-      if (a.mode == 1) {
-        const double da = dg - ds_all[k];
-        p0 += (a.beta - 1.0) * da;
-        p1 += stat_value(a, g * KP + perm[k]) * t;  // S * T: expec_log_x_cpp collapsed
-        p2 += lgamma(ph) - (ph - 1.0) * da;
+    } else {
+      const int w = v - 2 * cells;
+      const int what = w / (nf * K), fk = w - what * (nf * K);
+      const int f = fk / K, k = fk - f * K;
+      const int C = f == 0 ? Ca : Cb;
+      const size_t g0 = f == 0 ? g0a : g0b;
+      const int base = f == 0 ? 0 : cellsA;
+      const int bound = what == 0 ? min(C, a.n_cat_bound) : C;
+      double sum = 0;
+      for (int r = 0; r < bound; r++) sum += in_smem ? ph_s[base + r * K + k] : a.phi[(g0 + 1 + r) * KP + k];
+      if (what == 0) {
+        dsb[f * kMaxClasses + k] = dev_digamma(sum);  // mixdir_impl.cpp:61-72
+        a.T[g0 * KP + k] = 0.0;                       // NA row
+      } else if (what == 1) {
+        dsa[f * kMaxClasses + k] = dev_digamma(sum);  // R-level digamma(sum(phi_jk))
+      } else if (a.mode == 1) {
+        p2 -= lgamma(sum);
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int i = tid; i < cells; i += nt) {
+    const bool fa = i < cellsA;
+    const int f = fa ? 0 : 1;
+    const int ii = fa ? i : i - cellsA;
+    const int r = ii / K, k = ii - r * K;
+    const size_t g = (fa ? g0a : g0b) + 1 + r;
+    const double ph = in_smem ? ph_s[i] : a.phi[g * KP + k];
+    const double dg = in_smem ? dg_s[i] : dev_digamma(ph);
+    const double t = dg - dsb[f * kMaxClasses + k];  // mixdir_impl.cpp:80
+    a.T[g * KP + k] = t;
+    if (in_smem) ph_s[i] = t;
+    if (a.mode == 1) {
+      const double da = dg - dsa[f * kMaxClasses + k];
+      p0 += (a.beta - 1.0) * da;
+      p1 += stat_value(a, g * KP + perm[k]) * t;  // S * T: expec_log_x_cpp collapsed
+      p2 -= (ph - 1.0) * da;
+    }
+  }
+  __syncthreads();
   // unit table rows of this element: T2[g2][k] = T[src.x][k] + T[src.y][k]
   const int2 er = a.erange[blockIdx.x];
   if (a.t2src && er.y > 0) {
     for (int i = tid; i < er.y * KP; i += nt) {
       const int g2 = er.x + i / KP, k = i % KP;
       const int2 s = __ldg(&a.t2src[g2]);
-      double v = k < K ? a.T[(size_t)s.x * KP + k] : 0.0;
-      if (s.y >= 0 && k < K) v += a.T[(size_t)s.y * KP + k];
+      double v = 0.0;
+      if (k < K) {
+        if (in_smem) {  // source rows are rows of this element's features (row g0: NA, value 0)
+          const int ra = s.x - (int)g0a - 1;
+          if (ra >= 0) v = ph_s[ra * K + k];
+          if (s.y >= 0) {
+            const int rb = s.y - (int)g0b - 1;
+            if (rb >= 0) v += ph_s[cellsA + rb * K + k];
+          }
+        } else {
+          v = a.T[(size_t)s.x * KP + k];
+          if (s.y >= 0) v += a.T[(size_t)s.y * KP + k];
+        }
+      }
       a.T2[(size_t)g2 * KP + k] = v;
     }
   }
@@ -259,6 +338,23 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
       s1 += __ldcg(&a.part[(size_t)b * 3 + 1]);
       s2 += __ldcg(&a.part[(size_t)b * 3 + 2]);
     }
+    // the old prior's terms and the new class masses (permuted) come in while the sums settle
+    double* e1_s = ph_s;                    // [K]
+    double* e2_s = ph_s + kMaxClasses;      // [K]
+    double* cs_s = ph_s + 2 * kMaxClasses;  // [K] permuted class masses of the new zeta
+    const PriorState* st = a.st;  // still the prior this iteration's E-step used (old omega/kappa)
+    for (int k = tid; k < K; k += nt) {
+      e1_s[k] = st->e1[k];
+      e2_s[k] = a.dp ? st->e2[k] : 0.0;
+      cs_s[k] = stat_value(a, tab + perm[k]);
+    }
+    const double termA = st->termA, termE = st->termE;
+    const double H = a.stats[tab + KP], nna = a.stats[tab + KP + 2];
+    const double uf = a.stats[tab + KP + 1], bad = a.stats[tab + KP + 3];
+    IterStatus* s = a.status;
+    const int it = s->iter;
+    const int warn0 = s->warn;
+    const double prev = it > 0 ? a.trace[it - 1] : 0.0;
     __syncthreads();
     red[tid] = s0;
     red[kIterThreads + tid] = s1;
@@ -272,31 +368,23 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
       }
       __syncthreads();
     }
-    const double tC = red[0] + a.termC_const, tG = red[2 * kIterThreads];
-    const double tD = red[kIterThreads] + (double)K * a.stats[tab + KP + 2];  // +1 per NA cell per class
-    __syncthreads();
-    // class masses of the new zeta, permuted: what the next prior is built from
-    for (int k = tid; k < K; k += nt) red[k] = stat_value(a, tab + perm[k]);
-    __syncthreads();
     if (tid == 0) {
-      const PriorState* st = a.st;  // still the prior this iteration's E-step used (old omega/kappa)
+      const double tC = red[0] + a.termC_const, tG = red[2 * kIterThreads];
+      const double tD = red[kIterThreads] + (double)K * nna;  // +1 per NA cell per class
       double tB = 0;
       if (!a.dp) {
-        for (int k = 0; k < K; k++) tB += red[k] * st->e1[k];  // expec_log_zi, R/mixdir_vi.R:168-170
+        for (int k = 0; k < K; k++) tB += cs_s[k] * e1_s[k];  // expec_log_zi, R/mixdir_vi.R:168-170
       } else {
         double tail = 0;  // sum_{l>k} of the permuted class masses
         for (int k = K - 1; k >= 0; k--) {
-          tB += tail * st->e2[k] + red[k] * st->e1[k];  // dp_expec_log_zi, dp.R:202-211
-          tail += red[k];
+          tB += tail * e2_s[k] + cs_s[k] * e1_s[k];  // dp_expec_log_zi, dp.R:202-211
+          tail += cs_s[k];
         }
       }
-      const double H = a.stats[tab + KP];
-      const double elbo = st->termA + tB + tC + tD + st->termE + H + tG;
-      IterStatus* s = a.status;
-      const int it = s->iter;
-      int conv = 0, warn = s->warn;
+      const double elbo = termA + tB + tC + tD + termE + H + tG;
+      int conv = 0, warn = warn0;
       if (it != 0 && !isinf(elbo)) {
-        const double diff = elbo - a.trace[it - 1];
+        const double diff = elbo - prev;
         if (diff < -a.epsilon) warn |= 1;  // R/mixdir_vi.R:105-108
         if (diff < a.epsilon) conv = 1;    // R/mixdir_vi.R:109
       }
@@ -304,26 +392,27 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
       s->elbo = elbo;
       s->converged = conv;
       s->warn = warn;
-      s->underflow = (a.stats[tab + KP + 1] > 0.0) ? 1 : 0;
-      s->bad = (a.stats[tab + KP + 3] > 0.0) ? 1 : 0;
+      s->underflow = (uf > 0.0) ? 1 : 0;
+      s->bad = (bad > 0.0) ? 1 : 0;
       s->iter = it + 1;
       s->stop = (conv || s->underflow || s->bad) ? 1 : 0;
       *a.underflow_flag = 0;
     }
-    for (int k = tid; k < K; k += nt) a.cs_cur[k] = red[k];
+    for (int k = tid; k < K; k += nt) a.cs_cur[k] = cs_s[k];
     __syncthreads();
     if (a.stats_fixed) {  // the next E+M pass adds into S with atomics
       long long* z = reinterpret_cast<long long*>(a.stats);
       for (size_t i = tid; i < tab; i += nt) z[i] = 0;
     }
+    prior_step(a, cs_s, red);
+  } else {
+    prior_step(a, a.cs_cur, red);
   }
-  prior_step(a, a.cs_cur, red);
   if (tid == 0) {
     *a.ticket = 0u;
-    if (a.status_host && a.mode == 1) {
-      *a.status_host = *a.status;
-      __threadfence_system();
-    }
+    // mirror for the host's early-exit poll (posted write; the values the fit returns are read after
+    // the stream has drained, so no system-wide fence is paid here)
+    if (a.status_host && a.mode == 1) *a.status_host = *a.status;
   }
 }
 

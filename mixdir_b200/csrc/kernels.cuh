@@ -386,9 +386,20 @@ __global__ void __launch_bounds__(256) k_reduce_units(ReduceUnitsArgs a) {
   const int terms = m.count * a.n_clusters;
   double s = 0;
   if (k < a.KP) {
-    for (int t = warp; t < terms; t += 8) {
-      const int i = t / a.n_clusters, c = t - i * a.n_clusters;
-      s += a.Spart[(size_t)c * n2 + (size_t)(m.start + i * m.stride) * a.KP + k];
+    // eight independent loads in flight per thread, added in the same (index) order as before
+    for (int t0 = warp; t0 < terms; t0 += 64) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int t = t0 + 8 * u;
+        v[u] = 0.0;
+        if (t < terms) {
+          const int i = t / a.n_clusters, c = t - i * a.n_clusters;
+          v[u] = __ldcg(&a.Spart[(size_t)c * n2 + (size_t)(m.start + i * m.stride) * a.KP + k]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
     }
   }
   part[warp][lane] = s;

@@ -199,6 +199,35 @@ def test_underflow_is_an_error(dp):
                 eng.fit(2, [32.0, 32.0], p_big, dp=dp, max_iter=3)
 
 
+@pytest.mark.parametrize("engine", ENGINES, ids=ENGINE_IDS)
+def test_subnormal_band_is_renormalised_not_quantised(engine):
+    """A stated deviation (precision): the reference exponentiates the UNSHIFTED logit
+    (src/mixdir_impl.cpp:83) and normalises afterwards (R/mixdir_vi.R:82), so a row whose largest
+    logit lies in about [-745, -708] has subnormal, i.e. coarsely quantised, weights -- logits
+    (-740, -746) give zeta = (1, 0) in R.  The engine shifts by the row maximum and returns the
+    exact soft-max (0.99753, 0.00247); only the all-zero row (largest logit below -745.13) is the
+    reference's underflow error.  This test pins both sides of that statement."""
+    ncat = np.array([2], dtype=np.int32)
+    codes = np.array([[1], [2], [1]], dtype=np.uint8)
+    lp = np.array([0.0, 0.0])
+    #           class 0: r=1, r=2      class 1: r=1, r=2        (ragged (j,k,r) order)
+    T = np.array([-739.0, -2.0, -745.0, -3.0])  # logits row 1/3: (-740, -746); row 2: (-3, -4)
+    with Engine(codes, ncat) as eng:
+        out = eng.estep(2, lp, T, engine=engine, want_zeta=True)
+    assert out["underflow"] == 0
+    exact = 1.0 / (1.0 + np.exp(-6.0))
+    np.testing.assert_allclose(out["zeta"][0], [exact, 1.0 - exact], rtol=1e-12)
+    np.testing.assert_allclose(out["zeta"][1], [1.0 / (1.0 + np.exp(-1.0)), 1.0 - 1.0 / (1.0 + np.exp(-1.0))], rtol=1e-12)
+    # what the reference's arithmetic gives for row 1: exp(-740) is a subnormal, exp(-746) is 0
+    ref = np.exp(np.array([-740.0, -746.0]))
+    assert ref[0] > 0 and ref[1] == 0 and np.array_equal(ref / ref.sum(), [1.0, 0.0])
+    # one step further down the reference stops with its underflow error, and so does the engine
+    T2 = T.copy()
+    T2[0], T2[2] = -745.0, -751.0  # logits (-746, -752): rowSums(zeta) == 0
+    with Engine(codes, ncat) as eng:
+        assert eng.estep(2, lp, T2, engine=engine, want_zeta=True)["underflow"] == 1
+
+
 def test_create_from_r_matrix_and_u16():
     ncat = np.array([300, 4, 7], dtype=np.int32)  # > 255 levels -> 2-byte codes
     codes, _ = synth.make_codes(9, 500, ncat, 4, p_na=0.1)
