@@ -616,9 +616,18 @@ static int host_pack_threads() {
   return (int)std::max(1u, std::min(16u, hc ? hc : 1u));
 }
 
+// hostpack.cpp (built by g++): AVX2 packer for 1-byte codes
+extern "C" int mxd_have_avx2();
+extern "C" int mxd_pack_u8_avx2(const double* X, int64_t ld, int64_t r0, int64_t r1, int J, int row_bytes,
+                                unsigned char* dst, int limit);
+
 template <typename CT>
 static void pack_block(const double* X, int64_t ld, int64_t r0, int64_t r1, int J, int row_bytes,
                        unsigned char* dst /* row r0 of the chunk buffer */, int limit, int* bad) {
+  if (sizeof(CT) == 1 && mxd_have_avx2() && !getenv("MIXDIR_B200_SCALAR_PACK")) {
+    if (mxd_pack_u8_avx2(X, ld, r0, r1, J, row_bytes, dst, limit)) __atomic_store_n(bad, 1, __ATOMIC_RELAXED);
+    return;
+  }
   constexpr int64_t RB = 256;  // rows per block: 256 x J codes stay in L1 while the columns stream
   int b = 0;
   for (int64_t i0 = r0; i0 < r1; i0 += RB) {
@@ -1487,7 +1496,10 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
       const double e_cost = up.U * (KC / 16.0);
       const double m_cost = (fs ? 1.5 : (KC == 16 ? 1.6 : 1.5)) * rounds * W;
       const double ovh = KC == 16 ? 65.0 : 80.0;
-      const double wpen = W >= 15 ? 1.0 : (W >= 12 ? 1.05 : (W >= 8 ? 1.2 : 1.5));
+      // the time of a tile does not depend on the number of warps (each warp walks its own 16 rows and
+      // its own features; sweep 5..15 warps: time x warps constant), so fewer warps = smaller tiles cost
+      // proportionally more
+      const double wpen = (KC == 16 ? 15.0 : 20.0) / W;
       const double cost = P * (e_cost + m_cost + ovh) * wpen / used + P * 3000.0 / R;
       if (cost < best_cost) {
         best_cost = cost;
