@@ -100,7 +100,8 @@ int mixdir_b200_create(const void* codes, int code_bytes, int64_t n_rows, int n_
 /* Same from the reference's own representation of X: an n_rows x n_features
  * column-major double matrix, 1..C_j with NaN/NA for missing
  * (R/mixdir.R:117-118).  Packing to the compact code matrix happens inside: a few host threads
- * (MIXDIR_B200_HOST_THREADS, default min(16, cores)) write 1- or 2-byte codes into page-locked
+ * (MIXDIR_B200_HOST_THREADS, default min(16, cores / LOCAL_WORLD_SIZE); AVX2 when the CPU has it)
+ * write 1- or 2-byte codes into page-locked
  * staging buffers, chunk by chunk, and every chunk is copied to the device while the next one is
  * packed.  X may be pageable and is no longer needed when the call returns. */
 int mixdir_b200_create_from_r_matrix(const double* X, int64_t n_rows, int n_features,

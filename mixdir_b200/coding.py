@@ -22,6 +22,13 @@ def code_columns(columns, na_handle="ignore", levels=None):
 
     levels: optional explicit level lists (R factor input keeps its own levels,
     including unused ones, R/mixdir.R:100).
+
+    Level ORDER when levels are derived here: Python's sorted() over str(v).  R derives them with
+    as.factor(as.character(col)), i.e. R's number formatting (1.0 -> "1", here "1.0") and the
+    session locale's collation (mixed case orders differently from code-point order).  The order
+    only permutes the category axis of phi / category_prob; a caller that needs R's exact order
+    (to compare category_prob position by position) passes `levels` explicitly, which is what the
+    parity tests do.
     """
     if na_handle not in ("ignore", "category"):
         raise ValueError("na_handle must be 'ignore' or 'category'")  # match.arg, R/mixdir.R:91

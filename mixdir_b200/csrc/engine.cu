@@ -612,8 +612,14 @@ static int host_pack_threads() {
     const int t = atoi(e);
     if (t >= 1) return std::min(t, 64);
   }
-  const unsigned hc = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(16u, hc ? hc : 1u));
+  unsigned hc = std::thread::hardware_concurrency();
+  if (!hc) hc = 1;
+  // one process per GPU (torchrun): the ranks of a node share its cores
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+    const int lw = atoi(e);
+    if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
+  }
+  return (int)std::max(1u, std::min(16u, hc));
 }
 
 // hostpack.cpp (built by g++): AVX2 packer for 1-byte codes

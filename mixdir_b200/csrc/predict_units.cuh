@@ -213,13 +213,28 @@ __global__ void __launch_bounds__(512, 1) k_predict_units(PredictUnitArgs a) {
         double v = kreal ? q : -INFINITY;
         int i = (kreal && !(q != q)) ? kg : 0x7fffffff;  // NaN never wins (R which.max skips NA)
         if (i == 0x7fffffff) v = -INFINITY;
+        if (!a.pred_class) {
+          // (class_prob only: no arg-max)
+        } else if constexpr (KC == 32) {
+          // whole warp = one row: the bit pattern of q >= 0 orders like q; maximum of the high words,
+          // then of the low words among their holders (REDUX), first holder by ballot
+          const unsigned long long key = (i == 0x7fffffff) ? 0ull : (unsigned long long)__double_as_longlong(q) + 1ull;
+          const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+          const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+          const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+          const unsigned holders = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+          const int win = __ffs(holders) - 1;
+          i = (mh | ml) ? rank * KC + win : 0x7fffffff;
+          if (P > 1) v = __shfl_sync(0xffffffffu, v, win);
+        } else {
 #pragma unroll
-        for (int o = KC / 2; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-          if (ov > v || (ov == v && oi < i)) {
-            v = ov;
-            i = oi;
+          for (int o = KC / 2; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (ov > v || (ov == v && oi < i)) {
+              v = ov;
+              i = oi;
+            }
           }
         }
         bv[rg] = v;
