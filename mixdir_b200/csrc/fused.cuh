@@ -26,7 +26,7 @@
 //    they never share a feature inside a batch either.  Plain shared-memory
 //    read-modify-write, fp64.
 //  * flush: per-cluster partials to global, reduced in fixed order by
-//    k_reduce_partials (bit-reproducible run to run).
+//    k_reduce_units (bit-reproducible run to run).
 #pragma once
 
 #include "kernels.cuh"
