@@ -279,6 +279,7 @@ struct mixdir_b200_handle {
   bool scan_resolved = false;
   bool bad = false;  // the upload scan found an invalid code: every later call reports it
   mixdir_b200_timing timing = {};
+  bool time_em = true;  // CUDA events around every E+M pass (em_kernel_ms); off inside a concurrent batch
   // mixdir_b200_fit_batch: handles that share this one's uploaded data, each with its own stream and
   // workspace, one per concurrent fit (kept for later batches, freed with the handle)
   std::vector<mixdir_b200_handle*> views;
@@ -2140,7 +2141,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     RET_IF(ensure_units(h, s, pl));
     if (pl.engine == 5)  // the E+M kernel ADDS into the statistics; k_iter clears them after use
       CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
-    while ((int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
+    while (h->time_em && (int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreate(&e));
       s.ev_em.push_back(e);
@@ -2187,7 +2188,8 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     for (size_t si = 0; si < h->shards.size(); si++) {
       Shard& s = h->shards[si];
       int l = 0;
-      RET_IF(launch_em(h, s, K, pl, nullptr, true, s.ev_em[2 * it], s.ev_em[2 * it + 1], &l));
+      RET_IF(launch_em(h, s, K, pl, nullptr, true, h->time_em ? s.ev_em[2 * it] : nullptr,
+                       h->time_em ? s.ev_em[2 * it + 1] : nullptr, &l));
       stat_bufs[si] = s.d_stats;
       if (si == 0) l0 += l;
     }
@@ -2225,7 +2227,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     CU_TRY(cudaEventElapsedTime(&ms, s0.ev_loop0, s0.ev_loop1));
     h->timing.fit_loop_ms = ms;
     double em = 0;
-    for (int it = 0; it < iters; it++) {
+    for (int it = 0; h->time_em && it < iters; it++) {
       CU_TRY(cudaEventElapsedTime(&ms, s0.ev_em[2 * it], s0.ev_em[2 * it + 1]));
       em += ms;
     }
@@ -2355,8 +2357,10 @@ extern "C" int mixdir_b200_fit_batch(mixdir_b200_handle* h, const mixdir_b200_fi
     for (auto* v : h->views) {
       v->engine_pref = h->engine_pref;
       v->pairing = h->pairing;
+      v->time_em = false;  // (two event records per iteration and fit: host API calls the workers contend for)
     }
   }
+  h->time_em = C == 1;
   std::vector<int> st(n_fits, MIXDIR_B200_OK);
   std::vector<std::string> msg(n_fits);
   std::vector<mixdir_b200_timing> tms(C);
@@ -2396,6 +2400,7 @@ extern "C" int mixdir_b200_fit_batch(mixdir_b200_handle* h, const mixdir_b200_fi
     h->timing.iterations += tms[w].iterations; h->timing.em_launches += tms[w].em_launches;
     h->timing.total_launches += tms[w].total_launches;
   }
+  h->time_em = true;
   if (status) std::copy(st.begin(), st.end(), status);
   // an error in any repetition ends mixdir() (stop() inside mixdir_vi, R/mixdir.R:120-134)
   for (int i = 0; i < n_fits; i++)
