@@ -24,6 +24,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("MIXDIR_B200_TIME_EM", "1")  # per-pass kernel times also for small --rows
 import statistics
 import subprocess
 import sys

@@ -221,7 +221,9 @@ int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const double* log_pri
 /* ---- introspection for benchmarks ------------------------------------------ */
 typedef struct mixdir_b200_timing {
   double fit_loop_ms;   /* CUDA-event time of the iteration loop of the last fit (device 0) */
-  double em_kernel_ms;  /* summed CUDA-event time of the E+M kernel launches in that loop */
+  double em_kernel_ms;  /* summed CUDA-event time of the E+M kernel launches in that loop (0 for handles
+                           of fewer than 65,536 rows unless MIXDIR_B200_TIME_EM is set: the two event
+                           records per iteration cost a small fit several per cent) */
   int iterations;       /* iterations executed */
   int em_launches;      /* E+M kernel launches in the loop */
   int total_launches;   /* all kernel launches of the library inside the loop (per device) */

@@ -2093,6 +2093,12 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
   if (!colsum_init || !phi_init) return fail(MIXDIR_B200_BAD_ARGUMENT, "colsum_init / phi_init is NULL");
   DeviceGuard guard;
   const int K = p->n_latent, J = h->J;
+  // em_kernel_ms costs two event records per iteration: a few microseconds of a 40 us iteration on a
+  // small fit, nothing on a large one.  Small fits are timed only on request.
+  static const bool force_em_timing = getenv("MIXDIR_B200_TIME_EM") != nullptr;
+  const bool time_em_saved = h->time_em;
+  struct Restore { mixdir_b200_handle* h; bool v; ~Restore() { h->time_em = v; } } restore{h, time_em_saved};
+  if (h->time_em && !force_em_timing && h->n_rows < 65536) h->time_em = false;
   // the table needs n_cat = max(X) (R/mixdir_vi.R:8) before the first pass: when the caller
   // does not pass it, wait for the upload scan (no upload/compute overlap in that case)
   if (p->n_cat_bound <= 0) RET_IF(resolve_scan(h));

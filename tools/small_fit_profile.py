@@ -5,6 +5,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("MIXDIR_B200_TIME_EM", "1")  # small fits are not timed per pass by default
+
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
