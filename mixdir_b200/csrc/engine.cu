@@ -274,6 +274,8 @@ struct mixdir_b200_handle {
   std::vector<uint8_t> has_na;   // [J] 0: the feature holds no NA anywhere (valid once scan_resolved)
   std::vector<Shard> shards;
   int rank = 0, world = 1;   // multi-process flavour
+  int64_t row_offset = 0;    // global number of this rank's first row (seeds k_em_seg's rounding hash:
+                             // the same rows get the same rounding whatever the number of ranks)
   int engine_pref = 0;
   int pairing = 1;           // 1: pair features into units where shared memory allows (default)
   bool scan_resolved = false;
@@ -949,6 +951,26 @@ extern "C" int mixdir_b200_comm_destroy(mixdir_b200_comm* c) {
   return MIXDIR_B200_OK;
 }
 
+// multi-process flavour: the global number of this rank's first row = rows of the lower ranks
+// (one small all-reduce at create time; every rank creates its handles in the same order anyway)
+static int exchange_row_offset(mixdir_b200_handle* h) {
+  if (h->world <= 1) return MIXDIR_B200_OK;
+  Shard& s = h->shards[0];
+  CU_TRY(cudaSetDevice(s.device));
+  std::vector<long long> cnt(h->world, 0);
+  cnt[h->rank] = (long long)h->n_rows;
+  long long* d = nullptr;
+  RET_IF(dalloc(&d, (size_t)h->world));
+  CU_TRY(cudaMemcpyAsync(d, cnt.data(), cnt.size() * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+  NCCL_TRY(nccl::AllReduce(d, d, (size_t)h->world, nccl::kInt64, nccl::kSum, s.comm, s.stream));
+  CU_TRY(cudaMemcpyAsync(cnt.data(), d, cnt.size() * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+  CU_TRY(cudaStreamSynchronize(s.stream));
+  dfree(d);
+  h->row_offset = 0;
+  for (int r = 0; r < h->rank; r++) h->row_offset += cnt[r];
+  return MIXDIR_B200_OK;
+}
+
 extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, int64_t n_rows_local,
                                        int n_features, const int* ncat, mixdir_b200_comm* comm,
                                        mixdir_b200_handle** out) {
@@ -972,6 +994,7 @@ extern "C" int mixdir_b200_create_dist(const void* codes_local, int code_bytes, 
     s.comm = comm->comm;
     s.owns_comm = false;
     RET_IF(init_shard_static(h, s));
+    RET_IF(exchange_row_offset(h));
     return upload_codes(h, s, (const uint8_t*)codes_local);
   };
   if (st == MIXDIR_B200_OK) st = body();
@@ -1011,6 +1034,7 @@ extern "C" int mixdir_b200_create_dist_from_r_matrix(const double* X_local, int6
     s.comm = comm->comm;
     s.owns_comm = false;
     RET_IF(init_shard_static(h, s));
+    RET_IF(exchange_row_offset(h));
     return upload_r_matrix(h, s, X_local, n_rows_local);
   };
   if (st == MIXDIR_B200_OK) st = body();
@@ -1397,10 +1421,12 @@ static bool plan_units(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) 
 static int allreduce_stats(mixdir_b200_handle* h, std::vector<void*>& bufs, size_t tab, const Plan& pl) {
   if (!needs_allreduce(h)) return MIXDIR_B200_OK;
   if (pl.engine != 5) return allreduce(h, bufs, tab + pl.KP + 4, nccl::kDouble, nccl::kSum);
-  RET_IF(allreduce(h, bufs, tab, nccl::kInt64, nccl::kSum));
+  // k_em_seg: the statistics table AND the class masses are 64-bit integers (exact sums: N GPUs
+  // give the bits of one); only [H | underflow | nNA | bad] are doubles
+  RET_IF(allreduce(h, bufs, tab + 2 * pl.KP, nccl::kInt64, nccl::kSum));
   std::vector<void*> tails(bufs.size());
-  for (size_t i = 0; i < bufs.size(); i++) tails[i] = (double*)bufs[i] + tab;
-  return allreduce(h, tails, pl.KP + 4, nccl::kDouble, nccl::kSum);
+  for (size_t i = 0; i < bufs.size(); i++) tails[i] = (double*)bufs[i] + tab + 2 * pl.KP;
+  return allreduce(h, tails, 4, nccl::kDouble, nccl::kSum);
 }
 
 // engine 5: layout of the segment lists of a tile of R rows (seg.cuh).  fs: the features are dealt
@@ -1608,8 +1634,10 @@ static int plan_engine(mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   CU_TRY(cudaSetDevice(s.device));
   const int pref = h->engine_pref;
   // Automatic mode takes the segment kernel from 16384 rows on: below, rounding the responsibilities
-  // to 2^-31 can cost more than 1e-9 of the ELBO (seg.cuh), and such fits are launch-bound anyway.
-  const bool seg_ok = pref == 5 || h->n_rows * (int64_t)h->world >= 16384;
+  // to 32 bits can cost more than 1e-9 of the ELBO (seg.cuh), and such fits are launch-bound anyway.
+  // MIXDIR_B200_FP64_STATS=1 keeps fp64 statistics (unit kernel) in automatic mode.
+  static const bool fp64_stats = getenv("MIXDIR_B200_FP64_STATS") != nullptr;
+  const bool seg_ok = pref == 5 || (!fp64_stats && h->n_rows * (int64_t)h->world >= 16384);
   if ((pref == 0 || pref == 5) && seg_ok && plan_seg(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 5)
     return fail(MIXDIR_B200_BAD_ARGUMENT, "segment kernel does not fit this problem shape (K, sum C_j) "
@@ -1644,7 +1672,7 @@ static int ensure_workspace(mixdir_b200_handle* h, Shard& s, int K, const Plan& 
   RET_IF(dalloc(&s.d_T, tab));
   RET_IF(dalloc(&s.d_phi, tab));
   RET_IF(dalloc(&s.d_logU, tab));
-  RET_IF(dalloc(&s.d_stats, tab + KP + 4));
+  RET_IF(dalloc(&s.d_stats, tab + 2 * KP + 4));  // (k_em_seg: two words per class mass)
   RET_IF(dalloc(&s.d_logprior, KP));
   RET_IF(dalloc(&s.d_cs_a, kMaxClasses));
   RET_IF(dalloc(&s.d_part, (size_t)h->J * 3));
@@ -1893,9 +1921,10 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
 
   if (pl.engine >= 2 && s.n_rows > 0) {
     if (chunked) {  // partial buffers accumulate over the launches
-      if (pl.engine != 5)
+      if (pl.engine != 5) {
         CU_TRY(cudaMemsetAsync(s.d_Spart, 0, (size_t)pl.n_clusters * tab2 * sizeof(double), s.stream));
-      CU_TRY(cudaMemsetAsync(s.d_cspart, 0, (size_t)pl.n_clusters * pl.KP * sizeof(double), s.stream));
+        CU_TRY(cudaMemsetAsync(s.d_cspart, 0, (size_t)pl.n_clusters * pl.KP * sizeof(double), s.stream));
+      }
       CU_TRY(cudaMemsetAsync(s.d_Hpart, 0, (size_t)pl.n_clusters * pl.P * sizeof(double), s.stream));
     }
     if (ev0) CU_TRY(cudaEventRecord(ev0, s.stream));
@@ -1946,6 +1975,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
         g.codes = a.codes;
         g.seg = s.d_seg + (size_t)(r0 / pl.R) * pl.sp.TB;
         g.n_rows = nr;
+        g.row_base = h->row_offset + s.row0 + r0;
         g.n_tiles = n_tiles;
         g.WPR = up.WPRu;
         g.NR2 = up.NR2;
@@ -1969,9 +1999,9 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
         g.jobs = s.d_jobs;
         g.srow_to_stat = s.d_srow2stat;
         g.stats = reinterpret_cast<unsigned long long*>(s.d_stats);
-        g.stats_tail = s.d_stats + tab;
+        g.cs_fixed = g.stats + tab;
+        g.stats_tail = s.d_stats + tab + 2 * pl.KP;
         g.Hpart = s.d_Hpart;
-        g.cspart = s.d_cspart;
         g.n_hsum = (chunked ? pl.n_clusters : nclus) * pl.P;
         g.ticket = s.d_ticket;
         g.underflow = s.d_underflow;
@@ -2146,7 +2176,7 @@ extern "C" int mixdir_b200_fit(mixdir_b200_handle* h, const mixdir_b200_fit_para
     RET_IF(upload_ragoff(h, s, K));
     RET_IF(ensure_units(h, s, pl));
     if (pl.engine == 5)  // the E+M kernel ADDS into the statistics; k_iter clears them after use
-      CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
+      CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + 2 * pl.KP + 4) * sizeof(double), s.stream));
     while (h->time_em && (int)s.ev_em.size() < 2 * std::max(p->max_iter, 1)) {
       cudaEvent_t e;
       CU_TRY(cudaEventCreate(&e));
@@ -2905,7 +2935,6 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     RET_IF(pin_reset(s, (size_t)h->J * 8 + 4096 + unit_stage_bytes(pl.up) + seg_stage_bytes(pl.sp)));
     RET_IF(upload_ragoff(h, s, K));
     RET_IF(ensure_units(h, s, pl));
-    if (pl.engine == 5) CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + pl.KP + 4) * sizeof(double), s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_rag_a, table, rag * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemcpyAsync(s.d_logprior, lp.data(), pl.KP * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(IterStatus), s.stream));
@@ -2925,6 +2954,8 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
         RET_IF(launch_em(h, s, K, g, d_zeta, false, nullptr, nullptr, &l));
       }
     }
+    // k_em_seg ADDS into the statistics (and the generic pass above has used the buffer)
+    if (pl.engine == 5) CU_TRY(cudaMemsetAsync(s.d_stats, 0, (tab + 2 * pl.KP + 4) * sizeof(double), s.stream));
     RET_IF(launch_em(h, s, K, pl, pl.engine == 1 ? d_zeta : nullptr, true, nullptr, nullptr, &l));
     if (d_zeta) {
       CU_TRY(cudaMemcpy2DAsync(zeta + s.row0, (size_t)h->n_rows * sizeof(double), d_zeta,
@@ -2946,14 +2977,22 @@ extern "C" int mixdir_b200_estep(mixdir_b200_handle* h, int n_latent, const doub
     ScatterRagArgs ra = {h->J, K, pl.KP, s.d_ncat, s.d_rowoff, s.d_ragoff, nullptr, s.d_stats, 0, 0.0};
     k_table_to_ragged<<<jk_grid, 128, 0, s.stream>>>(ra, s.d_rag_b);
     CU_TRY(cudaGetLastError());
-    std::vector<double> tail(pl.KP + 2);
+    const int csw = pl.engine == 5 ? 2 : 1;  // k_em_seg: two integer words per class mass (seg.cuh)
+    std::vector<double> tail(csw * pl.KP + 2);
     if (S) CU_TRY(cudaMemcpyAsync(S, s.d_rag_b, rag * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CU_TRY(cudaMemcpyAsync(tail.data(), s.d_stats + tab, (pl.KP + 2) * sizeof(double),
+    CU_TRY(cudaMemcpyAsync(tail.data(), s.d_stats + tab, tail.size() * sizeof(double),
                            cudaMemcpyDeviceToHost, s.stream));
     CU_TRY(cudaStreamSynchronize(s.stream));
-    if (colsum) memcpy(colsum, tail.data(), K * sizeof(double));
-    if (entropy) *entropy = tail[pl.KP];
-    if (underflow) *underflow = tail[pl.KP + 1] > 0 ? 1 : 0;
+    if (colsum) {
+      if (pl.engine == 5) {
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(tail.data());
+        for (int k = 0; k < K; k++) colsum[k] = cs_value(w[k], w[pl.KP + k]);
+      } else {
+        memcpy(colsum, tail.data(), K * sizeof(double));
+      }
+    }
+    if (entropy) *entropy = tail[csw * pl.KP];
+    if (underflow) *underflow = tail[csw * pl.KP + 1] > 0 ? 1 : 0;
   }
   h->timing.engine = pl.engine;
   h->timing.classes_per_cta = pl.KC;

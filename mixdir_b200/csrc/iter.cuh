@@ -30,7 +30,8 @@ struct IterArgs {
                       // 1: full iteration step from the statistics buffer
   int n_cat_bound;    // loop bound of the digamma-sum (mixdir_impl.cpp:65 quirk)
   int NR, NR2;
-  int stats_fixed;    // 1: S is int64 fixed point (scale 2^-31, k_em_seg); 0: doubles
+  int stats_fixed;    // 1 (k_em_seg): S is int64 fixed point (units of 1 / (2^32 - 1)), the class masses
+                      // two int64 words each (seg.cuh: cs_value), the tail follows them; 0: doubles
   double beta, a1, a2, epsilon;
   double termC_const; // K * sum_j [lgamma(C_j beta) - C_j lgamma(beta)]: expec_log_ujk, R/mixdir_vi.R:172-174
   double termA_const; // dp=0: lgamma(K alpha) - K lgamma(alpha), R/mixdir_vi.R:164-166
@@ -56,8 +57,15 @@ struct IterArgs {
 };
 
 __device__ __forceinline__ double stat_value(const IterArgs& a, size_t i) {
-  if (a.stats_fixed && i < (size_t)a.NR * a.KP) return (double)reinterpret_cast<const long long*>(a.stats)[i] * 4.656612873077392578125e-10;
+  if (a.stats_fixed && i < (size_t)a.NR * a.KP) return (double)reinterpret_cast<const long long*>(a.stats)[i] * kFixedInv;
   return a.stats[i];
+}
+// class mass of class k: doubles behind the table, or k_em_seg's two integer words (seg.cuh: cs_value)
+__device__ __forceinline__ double mass_value(const IterArgs& a, int k) {
+  const size_t tab = (size_t)a.NR * a.KP;
+  if (!a.stats_fixed) return a.stats[tab + k];
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a.stats) + tab;
+  return ((double)w[k] * 2147483648.0 + (double)w[a.KP + k]) * (1.0 / 4611686018427387904.0);
 }
 
 // omega / kappa, prior logits and the ELBO terms A and E from the class masses cs[K].
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
   for (int k = tid; k < K; k += nt) perm[k] = k;
   __syncthreads();
   if (a.dp && a.mode == 1) {
-    for (int k = tid; k < K; k += nt) red[k] = stat_value(a, tab + k);
+    for (int k = tid; k < K; k += nt) red[k] = mass_value(a, k);
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
       const double c = red[k];
@@ -346,11 +354,12 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
     for (int k = tid; k < K; k += nt) {
       e1_s[k] = st->e1[k];
       e2_s[k] = a.dp ? st->e2[k] : 0.0;
-      cs_s[k] = stat_value(a, tab + perm[k]);
+      cs_s[k] = mass_value(a, perm[k]);
     }
     const double termA = st->termA, termE = st->termE;
-    const double H = a.stats[tab + KP], nna = a.stats[tab + KP + 2];
-    const double uf = a.stats[tab + KP + 1], bad = a.stats[tab + KP + 3];
+    const size_t tail = tab + (size_t)(a.stats_fixed ? 2 : 1) * KP;  // [H | underflow | nNA | bad]
+    const double H = a.stats[tail], nna = a.stats[tail + 2];
+    const double uf = a.stats[tail + 1], bad = a.stats[tail + 3];
     IterStatus* s = a.status;
     const int it = s->iter;
     const int warn0 = s->warn;
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(kIterThreads) k_iter(IterArgs a) {
     __syncthreads();
     if (a.stats_fixed) {  // the next E+M pass adds into S with atomics
       long long* z = reinterpret_cast<long long*>(a.stats);
-      for (size_t i = tid; i < tab; i += nt) z[i] = 0;
+      for (size_t i = tid; i < tab + 2 * (size_t)KP; i += nt) z[i] = 0;
     }
     prior_step(a, cs_s, red);
   } else {

@@ -34,6 +34,10 @@ namespace cg = cooperative_groups;
 // exp(x) == 0 in fp64 for x below ln(2^-1075); a row whose largest logit is
 // below this has rowSums(zeta) == 0 in the reference (R/mixdir_vi.R:77).
 __device__ constexpr double kExpUnderflow = -745.13321910194122211;
+// k_em_seg's fixed point for the responsibilities that feed phi: zeta in [0, 1] -> [0, 2^32 - 1]
+// (a full 32-bit word, no clamp at zeta = 1); sums of them are exact 64-bit integers
+constexpr double kFixedScale = 4294967295.0;
+constexpr double kFixedInv = 1.0 / 4294967295.0;
 constexpr int kMaxClasses = 256;  // K limit of the engine (8 classes per lane in the generic kernel)
 constexpr int kRowPad = 512;      // zero rows appended to the code matrix
 

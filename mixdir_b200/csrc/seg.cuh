@@ -18,14 +18,19 @@
 // conflict-free), adds them up in registers and touches the histogram once per (tile, feature,
 // code) instead of once per row.  Per (row, feature, class) that moves 4 bytes:
 //
-//   * zeta enters the M-step as 32-bit FIXED POINT, round-to-nearest(zeta * 2^31), and all sums are
-//     64-bit INTEGERS -- exact and order-independent, so the phi statistics are bit-identical whatever
-//     the tile order, grid size or number of GPUs (SURVEY 8e recommends exactly this).  Stated
-//     precision of the per-row math: logits, soft-max, entropy and the class masses colSums(zeta)
-//     (they order the classes of the DP variant and enter omega/kappa/lambda) in fp64 as before; the
-//     responsibilities that feed phi are rounded to 2^-31 (absolute error <= 2.4e-10 per entry,
-//     unbiased).  The resulting ELBO error is ~1e-10 / sqrt(rows) of its natural scale rows x
-//     features, which is why the automatic engine choice takes this kernel only from 16384 rows on.
+//   * zeta enters the M-step as 32-bit FIXED POINT, floor(zeta * (2^32 - 1) + u) with u in [0, 1) a
+//     hash of (row, class) -- stochastic, i.e. UNBIASED rounding -- and all sums are 64-bit INTEGERS:
+//     exact and order-independent, so the phi statistics are bit-identical whatever the tile order
+//     or grid size (SURVEY 8e recommends exactly this).  Stated precision of the per-row math:
+//     logits, soft-max, entropy and the class masses colSums(zeta) (they order the classes of the DP
+//     variant and enter omega/kappa/lambda) in fp64 as before; the responsibilities that feed phi
+//     carry zero-mean noise of 2^-32 per entry.  (Round-to-nearest was measured first: it sends
+//     every responsibility below half a unit to 0, a one-sided error that enters the ELBO's data
+//     term weighted with logits of -25 .. -100: 5e-9 .. 9e-9 relative at K = 32 whatever the number
+//     of rows.)  What remains is noise of ~1e-11 .. 1e-10 of the ELBO that the coordinate ascent
+//     itself amplifies while classes merge (profiles/r02_seg_precision.txt);
+//     the automatic engine choice takes this kernel only from 16384 rows on, and
+//     mixdir_b200_set_engine(h, 4) selects fp64 statistics.
 //   * no partial buffers and no reduction kernel: every CTA adds its histogram slice to the global
 //     int64 statistics with RED.ADD.U64; the last CTA to finish (atomic ticket) sums the per-CTA
 //     entropy partials in index order and writes the tail of the statistics buffer.
@@ -48,14 +53,37 @@
 
 namespace mxd {
 
-constexpr double kFixedScale = 2147483648.0;              // 2^31
-constexpr double kFixedInv = 4.656612873077392578125e-10; // 2^-31
+// u in [0, 1): a 32-bit mix of (row, class); the same (row, class) always gets the same u, so a fit is
+// reproducible run to run and independent of tile order and grid size
+__device__ __forceinline__ double round_dither(int64_t row, int k) {
+  uint32_t h = (uint32_t)row * 0x9E3779B1u + (uint32_t)(row >> 32) * 0x85EBCA77u + (uint32_t)k * 0xC2B2AE3Du;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  h *= 0x297A2D39u;
+  h ^= h >> 15;
+  return (double)h * 2.3283064365386963e-10;  // 2^-32
+}
+
+// Class masses colSums(zeta) order the classes of the DP variant (R/mixdir_vi_dp.R:97) and enter
+// omega / kappa / lambda: they keep full precision.  A responsibility zeta in [0, 1] becomes the 63-bit
+// integer q = round(zeta * 2^62), split into q >> 31 and q & (2^31 - 1); both words are summed as
+// 64-bit integers (no overflow below 2^32 rows per class, all GPUs together) -- exact and order-
+// independent like the statistics, resolution 2^-62 per entry (fp64 sums of a few hundred terms carry
+// more rounding error than that).  value = (hi * 2^31 + lo) * 2^-62.
+constexpr double kCsScale = 4611686018427387904.0;  // 2^62
+constexpr double kCsInv = 1.0 / 4611686018427387904.0;
+__host__ __device__ __forceinline__ double cs_value(unsigned long long hi, unsigned long long lo) {
+  return ((double)hi * 2147483648.0 + (double)lo) * kCsInv;
+}
+
 constexpr int kSegDummyRow = 255;
 
 struct SegArgs {
   const uint32_t* codes;      // packed unit codes, tile-transposed [tile][WPR][R] (as k_em_units)
   const unsigned char* seg;   // [n_tiles][TB] segment lists
   int64_t n_rows;
+  int64_t row_base;           // global number of the first row of this launch (seeds the rounding hash)
   int n_tiles;
   int WPR;
   int NR2;                    // rows of the global unit table
@@ -76,9 +104,10 @@ struct SegArgs {
                               //  first statistics row (inside the owner's table)}
   const int* srow_to_stat;    // shared-memory statistics row -> feature-table row
   unsigned long long* stats;  // [NR*KP] fixed-point sums, added with atomics
-  double* stats_tail;         // [cs : KP | H | underflow | nNA | bad] doubles, written by the last CTA
+  unsigned long long* cs_fixed;  // [2][KP] class masses colSums(zeta) as TWO-WORD fixed point (see
+                              // cs_split), added with atomics: rows NR and NR + 1 of the table
+  double* stats_tail;         // [H | underflow | nNA | bad] doubles, written by the last CTA
   double* Hpart;              // [>= gridDim.x] per-CTA entropy partials
-  double* cspart;             // [>= gridDim.x][KC] per-CTA class masses
   int n_hsum;                 // CTA partials the last CTA adds up (in index order)
   unsigned int* ticket;
   int* underflow;
@@ -239,7 +268,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
   const uint32_t zbase = smem_u32(z_s) + lane * 4;  // KC = 16 without FS: slot 1 reads the second copy
   uint32_t* z_peer = FS ? cluster.map_shared_rank(z_s, rank ^ 1) : nullptr;
   const uint32_t seg_addr = smem_u32(seg_s);
-  double csacc = 0, hacc = 0;
+  double hacc = 0;
+  unsigned long long cs_hi = 0ull, cs_lo = 0ull;  // class mass of (this lane's rows, class kg): cs_split
   int uflag = 0;
   const double kTiny = DBL_MIN * log(DBL_MIN);
   const int wrow0 = warp * RW;
@@ -350,10 +380,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       if (valid && kreal) {
         zz = ez[rg] * f;  // zeta / rowSums(zeta)
         hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - logs) : kTiny;  // R/mixdir_vi.R:181-184
-        csacc += zz;
+        if (zz > 0.0) {  // (NaN: an underflowing row, the pass is discarded)
+          const unsigned long long q = __double2ull_rn(zz * kCsScale);
+          cs_hi += q >> 31;
+          cs_lo += q & 0x7fffffffull;
+        }
       }
-      // the responsibility as the M-step sees it: fixed point, 2^-31 (NaN -> 0)
-      const uint32_t zf = __double2uint_rn(zz * kFixedScale);
+      // the responsibility as the M-step sees it: 32-bit fixed point (NaN -> 0), rounded
+      // stochastically (see the header): floor(zeta (2^32 - 1) + u), u = hash(row, class) in [0, 1)
+      const uint32_t zf = __double2uint_rd(fma(zz, kFixedScale, round_dither(a.row_base + (int64_t)t * R + row_in_tile0 + rg, kg)));
       if (FS) {  // both CTAs get the whole row: column = global class
         z_s[(row_in_tile0 + rg) * 32 + kg] = zf;
         z_peer[(row_in_tile0 + rg) * 32 + kg] = zf;
@@ -453,17 +488,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       }
     }
 #pragma unroll
-    for (int o = KC; o < 32; o <<= 1) csacc += __shfl_xor_sync(0xffffffffu, csacc, o);
+    for (int o = KC; o < 32; o <<= 1) {
+      cs_hi += __shfl_xor_sync(0xffffffffu, cs_hi, o);
+      cs_lo += __shfl_xor_sync(0xffffffffu, cs_lo, o);
+    }
     hacc = warp_sum(hacc);
-    if (slot == 0) red_s[warp * KC + kc] = csacc;
+    unsigned long long* redi_s = reinterpret_cast<unsigned long long*>(red_s);
+    for (int word = 0; word < 2; word++) {  // the two words of the class masses, one after the other
+      if (slot == 0) redi_s[warp * KC + kc] = word ? cs_lo : cs_hi;
+      __syncthreads();
+      if (threadIdx.x < KC) {
+        unsigned long long c = 0ull;
+        for (int w = 0; w < W; w++) c += redi_s[w * KC + threadIdx.x];
+        if (c) atomicAdd(&a.cs_fixed[word * KP + rank * KC + threadIdx.x], c);
+      }
+      __syncthreads();
+    }
     if (lane == 0) red_s[W * KC + warp] = hacc;
     __syncthreads();
-    if (threadIdx.x < KC) {
-      double c = 0;
-      for (int w = 0; w < W; w++) c += red_s[w * KC + threadIdx.x];
-      double* dst = &a.cspart[(size_t)blockIdx.x * KC + threadIdx.x];
-      *dst = a.accumulate ? *dst + c : c;
-    }
     if (threadIdx.x == 0) {
       double h = 0;
       for (int w = 0; w < W; w++) h += red_s[W * KC + w];
@@ -475,21 +517,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
     __shared__ int is_last;
     if (threadIdx.x == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (is_last) {  // fixed-order sums of the per-CTA partials: class masses, entropy; flags
+    if (is_last) {  // fixed-order sum of the per-CTA entropy partials; flags
       __threadfence();
-      const int ncl = a.n_hsum / P;
-      for (int k = threadIdx.x; k < KP; k += blockDim.x) {
-        double c = 0;
-        for (int cl = 0; cl < ncl; cl++) c += __ldcg(&a.cspart[((size_t)cl * P + k / KC) * KC + k % KC]);
-        a.stats_tail[k] = c;
-      }
       if (threadIdx.x == 0) {
         double h = 0;
         for (int c = 0; c < a.n_hsum; c++) h += __ldcg(&a.Hpart[c]);
-        a.stats_tail[KP] = h;
-        a.stats_tail[KP + 1] = __ldcg(a.underflow) ? 1.0 : 0.0;
-        a.stats_tail[KP + 2] = (double)a.scan->n_missing;
-        a.stats_tail[KP + 3] = a.scan->bad ? 1.0 : 0.0;
+        a.stats_tail[0] = h;
+        a.stats_tail[1] = __ldcg(a.underflow) ? 1.0 : 0.0;
+        a.stats_tail[2] = (double)a.scan->n_missing;
+        a.stats_tail[3] = a.scan->bad ? 1.0 : 0.0;
         *a.ticket = 0u;
       }
     }

@@ -96,6 +96,8 @@ def main():
             "ranks_agree": bool(all(f[1] == flags[0][1] and f[2] == flags[0][2] for f in flags)),
             "predict_equals_fit_final_pass": bool(all(f[0] for f in flags)),
             "elbo_rel_vs_single": rel(r["convergence"], s["convergence"]),
+            # k_em_seg: statistics and class masses are exact integer sums -> same bits on 1 and N GPUs
+            "phi_bit_identical_vs_single": bool(np.array_equal(r["phi"], s["phi"])),
             "elbo_rel_vs_oracle": rel(r["convergence"], ref["convergence"]),
             "phi_rel_vs_oracle": rel(r["phi"], ref["phi"]),
             "class_prob_abs_vs_oracle": float(np.max(np.abs(cp_all - ref["class_prob"]))),
@@ -105,7 +107,8 @@ def main():
         case["ok"] = bool(case["n_missing_ok"] and case["ranks_agree"] and case["predict_equals_fit_final_pass"]
                           and case["elbo_rel_vs_single"] < 1e-11 and case["elbo_rel_vs_oracle"] < 1e-9
                           and case["phi_rel_vs_oracle"] < 1e-7 and case["class_prob_abs_vs_oracle"] < 1e-6
-                          and case["pred_class_identical_vs_single"] and case["pred_class_identical_vs_oracle"])
+                          and case["pred_class_identical_vs_single"] and case["pred_class_identical_vs_oracle"]
+                          and (case["phi_bit_identical_vs_single"] or used != 5))
         report["cases"].append(case)
     if rank == 0:
         report["ok"] = bool(all(c["ok"] for c in report["cases"]))

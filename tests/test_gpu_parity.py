@@ -17,15 +17,16 @@ ELBO_RTOL = 1e-9  # ELBO, relative         (north_star)
 # seg (default: sorted-segment M-step)
 ENGINES = [1, 2, 4, 5]
 ENGINE_IDS = ["generic", "fused", "units", "seg"]
-# Engine 5 feeds the M-step with responsibilities rounded to 2^-31 (seg.cuh; exact integer sums).  The
-# north_star tolerances (ELBO 1e-9 relative, class_prob 1e-6, identical pred_class) apply unchanged;
-# the statistics themselves carry an absolute error of up to ~2.4e-10 * sqrt(rows) per cell.
+# Engine 5 feeds the M-step with responsibilities in 32-bit fixed point, rounded without bias
+# (seg.cuh; exact integer sums).  The north_star tolerances (ELBO 1e-9 relative, class_prob 1e-6,
+# identical pred_class) apply unchanged on every fixture; the statistics themselves carry zero-mean
+# noise of ~2^-32 * sqrt(rows of the cell) (test_seg_kernel_drift_is_bounded looks at long traces).
 SEG_S_ATOL = 1e-6
 
 
 def elbo_tol(engine, n_rows):
     """north_star's 1e-9, except for engine 5 FORCED onto fewer than 16384 rows (the automatic choice
-    takes it only from there on): rounding the responsibilities to 2^-31 perturbs the ELBO by
+    takes it only from there on): rounding the responsibilities to 32 bits perturbs the ELBO by
     ~1e-10 / sqrt(rows) of its natural scale rows x features, and the first, far-from-converged
     iterations of a random start amplify the perturbation (seg.cuh)."""
     return 1e-6 if (engine == 5 and n_rows < 16384) else ELBO_RTOL
@@ -77,7 +78,10 @@ def test_fit_matches_golden(name, engine, mushroom):
     assert abs(r["ELBO"] - float(g["ELBO"])) <= elbo_tol(engine, N) * abs(float(g["ELBO"]))
     small_seg = engine == 5 and N < 16384  # see elbo_tol
     np.testing.assert_allclose(r["lambda_"], g["lambda_"], rtol=1e-7 if small_seg else 1e-9, atol=1e-12)
-    np.testing.assert_allclose(r["phi"], g["phi"], rtol=1e-8, atol=SEG_S_ATOL if engine == 5 else 1e-9)
+    # (engine 5: the ascent amplifies the 32-bit rounding noise of the responsibilities while classes
+    # merge; the north_star quantities below keep their tolerances)
+    np.testing.assert_allclose(r["phi"], g["phi"], rtol=1e-5 if engine == 5 else 1e-8,
+                               atol=1e-5 if engine == 5 else 1e-9)
     np.testing.assert_allclose(r["category_prob"], g["category_prob"], rtol=1e-8,
                                atol=1e-7 if engine == 5 else 1e-10)
     prior = np.concatenate([r["kappa1"], r["kappa2"]]) if dp else r["omega"]
@@ -226,6 +230,36 @@ def test_subnormal_band_is_renormalised_not_quantised(engine):
     T2[0], T2[2] = -745.0, -751.0  # logits (-746, -752): rowSums(zeta) == 0
     with Engine(codes, ncat) as eng:
         assert eng.estep(2, lp, T2, engine=engine, want_zeta=True)["underflow"] == 1
+
+
+def test_seg_kernel_drift_is_bounded():
+    """The price of the sorted-segment kernel's 32-bit responsibilities: over 25
+    iterations from a random start at K = 32 the ELBO trace stays within ~1e-10 of the fp64-statistics
+    kernel on most iterations; while classes merge the ascent amplifies the rounding noise for a few
+    iterations (survey over 36 starts, profiles/r02_seg_precision.txt: median of the per-fit maxima
+    4e-10, worst 2e-8), and the traces come together again (final difference <= 4e-10); pred_class
+    is identical.  With round-to-nearest instead of unbiased rounding the same runs sat at 5e-9 .. 9e-9
+    on EVERY late iteration -- that is what this test guards against."""
+    ncat = np.array([16, 12, 8, 4, 2, 10] * 4, dtype=np.int32)
+    N, K = 65_536, 32
+    meds, finals = [], []
+    for seed in (2, 3, 4):
+        codes, _ = synth.make_codes(seed, N, ncat, K, p_na=0.05)
+        z0 = synth.zeta_init(seed, N, K).sum(axis=0)
+        p0 = synth.phi_init(seed, ncat, K)
+        out = {}
+        for engine in (5, 4):
+            with Engine(codes, ncat) as eng:
+                eng.set_engine(engine)
+                out[engine] = eng.fit(K, z0, p0, max_iter=25, epsilon=-np.inf, want_class_prob=False)
+        d = np.abs(out[5]["convergence"] - out[4]["convergence"]) / np.abs(out[4]["convergence"])
+        assert np.array_equal(out[5]["pred_class"], out[4]["pred_class"])
+        assert d.max() < 1e-7            # the amplified transients
+        assert np.median(d) < ELBO_RTOL  # the typical iteration
+        assert d[-1] < ELBO_RTOL         # and the end of the fit
+        meds.append(np.median(d))
+        finals.append(d[-1])
+    assert np.median(meds) < 3e-10
 
 
 def test_create_from_r_matrix_and_u16():
