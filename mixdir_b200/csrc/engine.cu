@@ -157,6 +157,8 @@ struct UnitPlan {
 // engine 5 (k_em_seg): layout of a tile's segment lists (seg.cuh)
 struct SegPlan {
   bool fs = false;  // feature split: the two CTAs of a cluster own half of the features each
+  bool gs = false;  // global statistics: no statistics table in shared memory, every (tile, feature,
+                    // code) sum goes straight to the global table (RED.ADD.U64); what lets K = 64 fit
   int G = 0;        // group padding, entries
   int TB = 0;       // bytes per tile
   // per M-step owner (fs: 2, else 1): block inside a tile's lists, jobs, statistics rows
@@ -1431,10 +1433,11 @@ static int allreduce_stats(mixdir_b200_handle* h, std::vector<void*>& bufs, size
 
 // engine 5: layout of the segment lists of a tile of R rows (seg.cuh).  fs: the features are dealt
 // alternately to the two CTAs of a cluster (the C_j pattern of neighbouring features balances).
-static void layout_seg(const mixdir_b200_handle* h, int R, int G, bool fs, int W, SegPlan* sp) {
+static void layout_seg(const mixdir_b200_handle* h, int R, int G, bool fs, bool gs, int W, SegPlan* sp) {
   const int J = h->J;
   *sp = SegPlan();
   sp->fs = fs;
+  sp->gs = gs;
   sp->G = G;
   const int owners = fs ? 2 : 1;
   int blk = 0;
@@ -1455,11 +1458,12 @@ static void layout_seg(const mixdir_b200_handle* h, int R, int G, bool fs, int W
       cnt_bytes += (h->ncat[j] + 3) & ~3;
       sc += h->ncat[j];
     }
-    sp->SC[o] = sc;
+    sp->SC[o] = gs ? 0 : sc;
     int off = (cnt_bytes + 15) & ~15, c0 = 0, s0 = 0;
     for (int j : feats) {
-      sp->jobs.push_back(make_int4(off, c0, h->ncat[j] | (j << 8), s0));
-      for (int c = 1; c <= h->ncat[j]; c++) sp->srow_to_stat.push_back(h->rowoff[j] + c);
+      // first statistics row: inside the owner's shared-memory table, or (gs) of the global feature table
+      sp->jobs.push_back(make_int4(off, c0, h->ncat[j] | (j << 8), gs ? h->rowoff[j] + 1 : s0));
+      for (int c = 1; c <= h->ncat[j] && !gs; c++) sp->srow_to_stat.push_back(h->rowoff[j] + c);
       c0 += (h->ncat[j] + 3) & ~3;
       s0 += h->ncat[j];
       off += (R + (G - 1) * std::min(h->ncat[j], R) + 15) & ~15;
@@ -1483,6 +1487,11 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
                           ? h->has_na.data() : nullptr;
   Plan best;
   double best_cost = 1e300;
+  // MIXDIR_B200_SEG_GLOBAL_STATS=1: no statistics table in shared memory, every (tile, feature, code)
+  // sum goes to the global table with RED.ADD.U64.  That lets K = 32 run in ONE CTA (no cluster) and
+  // K = 64, J = 100 in clusters of 4 x 16 classes -- both measured SLOWER than the default plans
+  // (DESIGN.md section 8), so the variant stays an A/B switch and is never chosen automatically.
+  const bool force_gs = getenv("MIXDIR_B200_SEG_GLOBAL_STATS") != nullptr;
   const int kcs[2] = {32, 16};
   for (int KC : kcs) {
     if (fKC > 0 && KC != fKC) continue;
@@ -1495,9 +1504,10 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
       if (fW > 0 && W != fW) continue;
       const int R = W * RG * RPW;
       if (R > kSegDummyRow) continue;
+     for (int gs = force_gs ? 1 : 0; gs <= (force_gs ? 1 : 0); gs++) {
       Plan c;
       const bool fs = KC == 16 && P == 2 && !getenv("MIXDIR_B200_NO_FEATURE_SPLIT");
-      layout_seg(h, R, fs ? 4 : 4 * RPW, fs, W, &c.sp);
+      layout_seg(h, R, fs ? 4 : 4 * RPW, fs, gs != 0, W, &c.sp);
       const int maxSC = std::max(c.sp.SC[0], c.sp.SC[1]), maxJobs = std::max(c.sp.njobs[0], c.sp.njobs[1]);
       const int maxBlk = std::max(c.sp.blk_size[0], c.sp.blk_size[1]);
       UnitPlan up;
@@ -1538,6 +1548,7 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
         best_cost = cost;
         best = c;
       }
+     }
     }
   }
   if (best.engine != 5) return false;
@@ -1779,7 +1790,7 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
   std::vector<UnitDesc> sig = up.desc;  // element order + what the placement depends on
   sig.push_back(UnitDesc{pl.engine, pl.KC, up.Q, up.srows});
   sig.push_back(UnitDesc{pl.R, pl.RG, pl.W, pl.FPG});
-  sig.push_back(UnitDesc{pl.sp.fs ? 1 : 0, pl.sp.G, pl.sp.TB, 0});
+  sig.push_back(UnitDesc{pl.sp.fs ? 1 : 0, pl.sp.G, pl.sp.TB, pl.sp.gs ? 1 : 0});
   if (s.unit_valid && s.unit_sig.size() == sig.size() &&
       memcmp(s.unit_sig.data(), sig.data(), sig.size() * sizeof(UnitDesc)) == 0)
     return MIXDIR_B200_OK;
@@ -1989,6 +2000,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
           g.job0[o] = pl.sp.job0[o]; g.njobs[o] = pl.sp.njobs[o];
           g.sc0[o] = pl.sp.sc0[o]; g.SC[o] = pl.sp.SC[o];
         }
+        g.gs = pl.sp.gs ? 1 : 0;
         g.maxSC = std::max(pl.sp.SC[0], pl.sp.SC[1]);
         g.maxJobs = std::max(pl.sp.njobs[0], pl.sp.njobs[1]);
         g.maxBlk = std::max(pl.sp.blk_size[0], pl.sp.blk_size[1]);

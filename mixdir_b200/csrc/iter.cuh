@@ -65,7 +65,7 @@ __device__ __forceinline__ double mass_value(const IterArgs& a, int k) {
   const size_t tab = (size_t)a.NR * a.KP;
   if (!a.stats_fixed) return a.stats[tab + k];
   const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a.stats) + tab;
-  return ((double)w[k] * 2147483648.0 + (double)w[a.KP + k]) * (1.0 / 4611686018427387904.0);
+  return ((double)w[k] * 4294967296.0 + (double)w[a.KP + k]) * (1.0 / 4611686018427387904.0);
 }
 
 // omega / kappa, prior logits and the ELBO terms A and E from the class masses cs[K].

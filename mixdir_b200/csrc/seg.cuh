@@ -53,28 +53,35 @@
 
 namespace mxd {
 
-// u in [0, 1): a 32-bit mix of (row, class); the same (row, class) always gets the same u, so a fit is
-// reproducible run to run and independent of tile order and grid size
-__device__ __forceinline__ double round_dither(int64_t row, int k) {
-  uint32_t h = (uint32_t)row * 0x9E3779B1u + (uint32_t)(row >> 32) * 0x85EBCA77u + (uint32_t)k * 0xC2B2AE3Du;
+// Rounding dither: a 32-bit mix x of (global row, class), u = x / 2^32 in [0, 1).  The same (row,
+// class) always gets the same x, so a fit is reproducible run to run and independent of tile order,
+// grid size and the number of GPUs.  The lattice point row * C1 + class * C2 is computed once per tile
+// and lane (dither_base) and stepped by C1 per row; two xorshift-multiply rounds mix it (uniformity and
+// row / class correlations checked on the host, tools/dither_hash_check.py).
+constexpr uint32_t kDitherC1 = 0x9E3779B1u, kDitherC2 = 0xC2B2AE3Du;
+__device__ __forceinline__ uint32_t dither_base(int64_t row, int k) {
+  return (uint32_t)row * kDitherC1 + (uint32_t)(row >> 32) * 0x85EBCA77u + (uint32_t)k * kDitherC2;
+}
+__device__ __forceinline__ uint32_t dither_mix(uint32_t h) {
   h ^= h >> 15;
   h *= 0x2C1B3C6Du;
-  h ^= h >> 12;
+  h ^= h >> 13;
   h *= 0x297A2D39u;
-  h ^= h >> 15;
-  return (double)h * 2.3283064365386963e-10;  // 2^-32
+  return h;
 }
+// floor(zeta * (2^32 - 1) + x / 2^32) = floor(zeta * (2^32 - 1) * 2^32 + x) >> 32: one DFMA, one F2I
+constexpr double kFixedScale32 = 4294967295.0 * 4294967296.0;
 
 // Class masses colSums(zeta) order the classes of the DP variant (R/mixdir_vi_dp.R:97) and enter
 // omega / kappa / lambda: they keep full precision.  A responsibility zeta in [0, 1] becomes the 63-bit
-// integer q = round(zeta * 2^62), split into q >> 31 and q & (2^31 - 1); both words are summed as
-// 64-bit integers (no overflow below 2^32 rows per class, all GPUs together) -- exact and order-
-// independent like the statistics, resolution 2^-62 per entry (fp64 sums of a few hundred terms carry
-// more rounding error than that).  value = (hi * 2^31 + lo) * 2^-62.
+// integer q = round(zeta * 2^62), split into its two 32-bit halves; both are summed as 64-bit integers
+// (no overflow below 2^32 rows, all GPUs together) -- exact and order-independent like the
+// statistics, resolution 2^-62 per entry (fp64 sums of a few hundred terms carry more rounding error
+// than that).  value = (hi * 2^32 + lo) * 2^-62.
 constexpr double kCsScale = 4611686018427387904.0;  // 2^62
 constexpr double kCsInv = 1.0 / 4611686018427387904.0;
 __host__ __device__ __forceinline__ double cs_value(unsigned long long hi, unsigned long long lo) {
-  return ((double)hi * 2147483648.0 + (double)lo) * kCsInv;
+  return ((double)hi * 4294967296.0 + (double)lo) * kCsInv;
 }
 
 constexpr int kSegDummyRow = 255;
@@ -96,6 +103,8 @@ struct SegArgs {
   int job0[2], njobs[2];
   int sc0[2], SC[2];
   int maxSC, maxJobs, maxBlk;  // shared-memory sizing (maxima over the owners)
+  int gs;                     // 1: no shared-memory statistics table (SC = 0); jobs[].w is the feature's
+                              // first row of the GLOBAL table and every group sum is added there
   const int* eoff_rot;        // as k_em_units
   const int* slot_of_row;
   const double* T2;
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
   int it = 0;
   for (int t = cluster_id; t < a.n_tiles; t += n_clusters, ++it) {
     const uint32_t par = (uint32_t)(it & 1);
+    const uint32_t dbase = dither_base(a.row_base + (int64_t)t * R + row_in_tile0, kg);
     mbar_wait(&bar[0], par);
     const uint32_t* trow = tile_s + row_in_tile0;
 
@@ -380,15 +390,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       if (valid && kreal) {
         zz = ez[rg] * f;  // zeta / rowSums(zeta)
         hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - logs) : kTiny;  // R/mixdir_vi.R:181-184
-        if (zz > 0.0) {  // (NaN: an underflowing row, the pass is discarded)
-          const unsigned long long q = __double2ull_rn(zz * kCsScale);
-          cs_hi += q >> 31;
-          cs_lo += q & 0x7fffffffull;
-        }
       }
-      // the responsibility as the M-step sees it: 32-bit fixed point (NaN -> 0), rounded
-      // stochastically (see the header): floor(zeta (2^32 - 1) + u), u = hash(row, class) in [0, 1)
-      const uint32_t zf = __double2uint_rd(fma(zz, kFixedScale, round_dither(a.row_base + (int64_t)t * R + row_in_tile0 + rg, kg)));
+      zz = (zz > 0.0) ? zz : 0.0;  // NaN (an underflowing row: the pass is discarded) -> 0
+      {  // class mass: two-word integer (cs_value)
+        const unsigned long long q = __double2ull_rn(zz * kCsScale);
+        cs_hi += q >> 32;
+        cs_lo += q & 0xffffffffull;
+      }
+      // the responsibility as the M-step sees it: 32-bit fixed point, rounded stochastically (see the
+      // header): floor(zeta (2^32 - 1) + u), u = mix(row, class) / 2^32 in [0, 1)
+      const uint32_t zf = (uint32_t)(__double2ull_rd(
+          fma(zz, kFixedScale32, (double)dither_mix(dbase + (uint32_t)rg * kDitherC1))) >> 32);
       if (FS) {  // both CTAs get the whole row: column = global class
         z_s[(row_in_tile0 + rg) * 32 + kg] = zf;
         z_peer[(row_in_tile0 + rg) * 32 + kg] = zf;
@@ -415,14 +427,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       const int C = jd.z & 0xff;
       uint32_t p = seg_addr + (uint32_t)jd.x + (FS ? 0 : slot * 4);
       const uint32_t* cnt = reinterpret_cast<const uint32_t*>(seg_s + jd.y);  // 4-byte aligned
-      unsigned long long* srow = S_s + (size_t)jd.w * SW + (FS ? lane : kc);
+      unsigned long long* srow = S_s + (size_t)(a.gs ? 0 : jd.w) * SW + (FS ? lane : kc);
+      unsigned long long* grow = a.stats + (size_t)jd.w * KP + (FS ? lane : rank * KC + kc);  // (gs)
       uint32_t w = lds_u32(p);
       uint32_t cw = 0;
-      for (int c = 0; c < C; c++, srow += SW) {
+      for (int c = 0; c < C; c++, srow += SW, grow += KP) {
         if ((c & 3) == 0) cw = cnt[c >> 2];  // group sizes of four codes at a time
         const int n = (int)((cw >> (8 * (c & 3))) & 0xffu);
         if (n == 0) continue;  // warp-uniform
-        const unsigned long long old = *srow;  // early: its latency hides behind the loop
+        const unsigned long long old = a.gs ? 0ull : *srow;  // early: its latency hides behind the loop
         unsigned long long s0 = 0ull, s1 = 0ull;
         int g = 0;
         for (; g + 2 <= n; g += 2) {  // two list words (8 rows per slot) per round
@@ -453,7 +466,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
         }
         s0 += s1;
         if (MSLOTS == 2) s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-        if (FS || slot == 0) *srow = old + s0;
+        if (FS || slot == 0) {
+          if (!a.gs)
+            *srow = old + s0;
+          else if (s0)
+            atomicAdd(grow, s0);  // RED.E.ADD.64: 128 (256) contiguous bytes per warp instruction
+        }
       }
     }
     __syncthreads();  // zeta tile and segment lists may be overwritten

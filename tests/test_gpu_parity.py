@@ -262,6 +262,39 @@ def test_seg_kernel_drift_is_bounded():
     assert np.median(meds) < 3e-10
 
 
+def test_seg_global_statistics_variant(monkeypatch):
+    """MIXDIR_B200_SEG_GLOBAL_STATS=1 (A/B switch): k_em_seg without a statistics
+    table in shared memory -- K = 32 then runs in ONE CTA per SM, the S5 shape K = 64, J = 100 in
+    clusters of 4 x 16 classes.  Checked against the default plan (K = 32; another pair plan adds the
+    logit terms in another order, so the rounded responsibilities differ in their last unit here and
+    there) and against the fp64 unit kernel where the default plan does not fit (K = 64)."""
+    for K, J in ((32, 60), (64, 100)):
+        pat = np.array(([16, 12, 8, 4, 2, 10] * 20)[:J], dtype=np.int32)
+        N = 20_000
+        codes, _ = synth.make_codes(31, N, pat, 16, p_na=0.03)
+        z0 = synth.zeta_init(31, N, K).sum(axis=0)
+        p0 = synth.phi_init(31, pat, K)
+        out = {}
+        for tag, env, engine in (("default", None, 5 if K == 32 else 4), ("global", "1", 5)):
+            if env:
+                monkeypatch.setenv("MIXDIR_B200_SEG_GLOBAL_STATS", env)
+            else:
+                monkeypatch.delenv("MIXDIR_B200_SEG_GLOBAL_STATS", raising=False)
+            with Engine(codes, pat) as eng:
+                eng.set_engine(engine)
+                out[tag] = eng.fit(K, z0, p0, max_iter=6, epsilon=-np.inf)
+                t = eng.timing()
+            assert t["engine"] == engine
+            if tag == "global":
+                assert (t["cluster_size"], t["classes_per_cta"]) == ((1, 32) if K == 32 else (4, 16)), t
+        monkeypatch.delenv("MIXDIR_B200_SEG_GLOBAL_STATS", raising=False)
+        a, b = out["default"], out["global"]
+        assert np.array_equal(a["pred_class"], b["pred_class"])
+        assert rel(b["convergence"], a["convergence"]) < ELBO_RTOL
+        np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-5, atol=1e-5)
+        assert np.max(np.abs(a["class_prob"] - b["class_prob"])) < CP_ATOL
+
+
 def test_create_from_r_matrix_and_u16():
     ncat = np.array([300, 4, 7], dtype=np.int32)  # > 255 levels -> 2-byte codes
     codes, _ = synth.make_codes(9, 500, ncat, 4, p_na=0.1)

@@ -114,3 +114,21 @@ int main() {
                    check=True)
     worst, edges = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert float(worst) < 1.0 and edges == "1"
+
+
+def test_seg_kernel_rounding_dither_is_uniform_and_uncorrelated():
+    """k_em_seg rounds the responsibilities to 32 bits with a dither u = mix(row, class) / 2^32
+    (seg.cuh); the rounding is unbiased only if u is uniform and the noise of a statistics cell grows
+    like sqrt(rows) only if neighbouring rows / classes are uncorrelated.  tools/dither_hash_check.py
+    restates the mix; an independent uniform sample would give the same numbers."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "dither_hash_check", os.path.join(os.path.dirname(__file__), "..", "tools", "dither_hash_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.check(n_rows=100_000)
+    assert abs(r["mean"] - 0.5) < 1e-3 and abs(r["var_times_12"] - 1) < 5e-3
+    assert r["chi2_per_dof"] < 1.3
+    for k in ("corr_next_row", "corr_row_plus_8", "corr_row_plus_240", "corr_next_class"):
+        assert abs(r[k]) < 5e-3, k
+    assert abs(r["block_16_var_ratio"] - 1) < 0.05 and abs(r["block_240_var_ratio"] - 1) < 0.1
