@@ -132,3 +132,40 @@ def test_seg_kernel_rounding_dither_is_uniform_and_uncorrelated():
     for k in ("corr_next_row", "corr_row_plus_8", "corr_row_plus_240", "corr_next_class"):
         assert abs(r[k]) < 5e-3, k
     assert abs(r["block_16_var_ratio"] - 1) < 0.05 and abs(r["block_240_var_ratio"] - 1) < 0.1
+
+
+@pytest.mark.parametrize("J", [1, 3, 4, 7, 8, 12, 23, 60, 61])
+def test_host_packer_fp64_to_bytes(J):
+    """mixdir_b200_create_from_r_matrix's host packer (csrc/hostpack.cpp; host code, runs without a GPU):
+    the reference's fp64 column-major X with NA (R/mixdir.R:117-118) -> 1-byte row-major codes, 0 = NA;
+    every column-group path (8, 4, rest), ragged row counts, a row offset, padded rows; cells that are not
+    NA or an integer in 1..limit raise the flag and come out as 0."""
+    import ctypes as C
+    from mixdir_b200 import _capi
+    lib = _capi.lib()
+    if not lib.mxd_have_avx2():
+        pytest.skip("no AVX2 on this host")
+    fn = lib.mxd_pack_u8_avx2
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(J)
+    for N, r0, r1 in ((5000, 0, 5000), (4099, 13, 4099), (7, 0, 7), (2100, 256, 2049)):
+        X = np.asfortranarray(rng.integers(1, 200, size=(N, J)).astype(np.float64))
+        X[rng.random((N, J)) < 0.1] = np.nan
+        row_bytes = (J + 3) // 4 * 4
+        out = np.full((r1 - r0, row_bytes), 0xEE, dtype=np.uint8)
+        bad = fn(X.ctypes.data, N, r0, r1, J, row_bytes, out.ctypes.data, 255)
+        want = np.nan_to_num(X[r0:r1], nan=0.0).astype(np.uint8)
+        assert bad == 0
+        assert np.array_equal(out[:, :J], want)
+        assert (out[:, J:] == 0xEE).all()  # padding bytes are the caller's
+        # invalid cells: a fraction, a zero, a negative, a value above the limit
+        for v in (2.5, 0.0, -3.0, 256.0, np.inf):
+            Y = X.copy(order="F")
+            i, j = int(rng.integers(r0, r1)), int(rng.integers(0, J))
+            Y[i, j] = v
+            out2 = np.zeros_like(out)
+            assert fn(Y.ctypes.data, N, r0, r1, J, row_bytes, out2.ctypes.data, 255) == 1, v
+            want2 = want.copy()
+            want2[i - r0, j] = 0
+            assert np.array_equal(out2[:, :J], want2)
