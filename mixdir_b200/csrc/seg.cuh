@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       unsigned long long* grow = a.stats + (size_t)jd.w * KP + (FS ? lane : rank * KC + kc);  // (gs)
       uint32_t w = lds_u32(p);
       uint32_t cw = 0;
-      for (int c = 0; c < C; c++, srow += SW, grow += KP) {
+      for (int c = 0; c < C; c++, srow += SW) {
         if ((c & 3) == 0) cw = cnt[c >> 2];  // group sizes of four codes at a time
         const int n = (int)((cw >> (8 * (c & 3))) & 0xffu);
         if (n == 0) continue;  // warp-uniform
@@ -470,7 +470,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
           if (!a.gs)
             *srow = old + s0;
           else if (s0)
-            atomicAdd(grow, s0);  // RED.E.ADD.64: 128 (256) contiguous bytes per warp instruction
+            // 128 (256) contiguous bytes per warp instruction.  The address is formed per group (not
+            // stepped in place): stepping would wait for the atomic to have read its address registers
+            atomicAdd(grow + (size_t)c * KP, s0);
         }
       }
     }

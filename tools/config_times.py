@@ -1,5 +1,6 @@
 """Per-iteration and whole-fit times of the small BASELINE configs (M1, M2, S3) on the GPU next to the
-reference's CPU path (oracle/_ref + restated R loop, 1 thread).   python tools/config_times.py"""
+reference's CPU path (oracle/_ref + restated R loop, 1 thread).
+    python tools/config_times.py [--no-cpu]        (--no-cpu: skip the CPU leg, 40 s)"""
 import os
 import sys
 import time
@@ -18,7 +19,11 @@ g = load_golden("mushroom.npz")
 mush = dict(codes=g["codes"], categories=json.loads(str(g["categories"])))
 
 
+NO_CPU = "--no-cpu" in sys.argv
+
+
 def run(name, codes, ncat, K, dp, max_iter=100, eps=1e-3, cpu=True):
+    cpu = cpu and not NO_CPU
     N = codes.shape[0]
     z0 = synth.zeta_init(1, N, K)
     p0 = synth.phi_init(1, ncat, K)
@@ -30,7 +35,9 @@ def run(name, codes, ncat, K, dp, max_iter=100, eps=1e-3, cpu=True):
         tm = e.timing()
     wall = time.perf_counter() - t
     line = (f"{name:34s} GPU: {r['n_iter']:3d} iterations, {tm['fit_loop_ms'] / r['n_iter'] * 1e3:8.1f} us/iter on the "
-            f"device, whole mixdir_vi call (create+fit+results+destroy) {wall * 1e3:8.2f} ms, engine {tm['engine']}")
+            f"device, whole mixdir_vi call (create+fit+results+destroy) {wall * 1e3:8.2f} ms, engine {tm['engine']}"
+            f" (KC {tm['classes_per_cta']}, P {tm['cluster_size']}, {tm['grid_ctas']} CTAs"
+            + (f", E+M pass {tm['em_kernel_ms'] / r['n_iter'] * 1e3:.1f} us" if tm['em_kernel_ms'] > 0 else "") + ")")
     if cpu:
         t = time.perf_counter()
         ref = po.fit(po.codes_to_r_matrix(codes), ncat, K, int(dp), 1.0, 1.0, 0.1, max_iter, eps, z0, p0,

@@ -1,7 +1,8 @@
 """How far the ELBO trace of the sorted-segment kernel (engine 5: responsibilities rounded to 32-bit
 fixed point before they enter the phi statistics, exact integer sums) drifts from the fp64-statistics
 unit kernel (engine 4) on the same data and start: relative difference per iteration, over sizes, K
-and seeds.   python tools/seg_precision.py [quick]"""
+and seeds; and the largest class_prob difference when both fits stop after 6, 12 and 25 iterations
+(north_star: class_prob within 1e-6).   python tools/seg_precision.py [quick]"""
 import os
 import sys
 
@@ -15,8 +16,9 @@ ncat = np.array([16, 12, 8, 4, 2, 10] * 4, dtype=np.int32)
 cases = [(32, 16384, range(2, 4)), (10, 70000, range(2, 4))] if quick else \
     [(32, 16384, range(2, 10)), (32, 65536, range(2, 18)), (32, 300000, range(2, 6)), (32, 2000000, range(2, 4)),
      (10, 70000, range(2, 6)), (64, 100000, range(2, 4))]
+# (K = 64 runs on the fp64 unit kernel by default; MIXDIR_B200_SEG_GLOBAL_STATS=1 puts it on k_em_seg)
 for K, N, seeds in cases:
-    mx, fin, med = [], [], []
+    mx, fin, med, cpmax = [], [], [], []
     for seed in seeds:
         codes, _ = synth.make_codes(seed, N, ncat, K, p_na=0.05)
         z0 = synth.zeta_init(seed, min(N, 65536), K).sum(0) * (N / min(N, 65536))
@@ -30,7 +32,19 @@ for K, N, seeds in cases:
         rel = np.abs(a - b) / np.abs(b)
         same = np.array_equal(out[5]["pred_class"], out[4]["pred_class"])
         mx.append(rel.max()); fin.append(rel[-1]); med.append(np.median(rel))
+        cps = []
+        if N <= 300000 and seed < 6:
+            for stop in (6, 12, 25):
+                cp = {}
+                for eng_id in (5, 4):
+                    with Engine(codes, ncat) as e:
+                        e.set_engine(eng_id)
+                        cp[eng_id] = e.fit(K, z0, p0, max_iter=stop, epsilon=-np.inf, want_pred_class=False)["class_prob"]
+                cps.append(f"{np.max(np.abs(cp[5] - cp[4])):.1e}")
+                cpmax.append(float(np.max(np.abs(cp[5] - cp[4]))))
         print(f"K={K} N={N} seed={seed}: max {rel.max():.2e} (iteration {rel.argmax() + 1}), median {np.median(rel):.2e}, "
-              f"after 25 iterations {rel[-1]:.2e}, pred_class identical {same}", flush=True)
+              f"after 25 iterations {rel[-1]:.2e}, pred_class identical {same}"
+              + (f", class_prob max abs diff after 6/12/25 iterations {'/'.join(cps)}" if cps else ""), flush=True)
     print(f"== K={K} N={N}: over {len(mx)} starts: worst max {max(mx):.2e}, median of the maxima {np.median(mx):.2e}, "
-          f"worst final {max(fin):.2e}, median of the per-fit medians {np.median(med):.2e}", flush=True)
+          f"worst final {max(fin):.2e}, median of the per-fit medians {np.median(med):.2e}"
+          + (f", class_prob: worst {max(cpmax):.1e}, median {np.median(cpmax):.1e}" if cpmax else ""), flush=True)
