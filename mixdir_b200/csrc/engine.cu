@@ -27,6 +27,7 @@
 #include "fused.cuh"
 #include "units.cuh"
 #include "seg.cuh"
+#include "seg_ws.cuh"
 #include "iter.cuh"
 #include "predict.cuh"
 #include "predict_units.cuh"
@@ -157,6 +158,7 @@ struct UnitPlan {
 // engine 5 (k_em_seg): layout of a tile's segment lists (seg.cuh)
 struct SegPlan {
   bool fs = false;  // feature split: the two CTAs of a cluster own half of the features each
+  bool ws = false;  // warp-specialised kernel (seg_ws.cuh): fs only, 1024 threads per CTA
   bool gs = false;  // global statistics: no statistics table in shared memory, every (tile, feature,
                     // code) sum goes straight to the global table (RED.ADD.U64); what lets K = 64 fit
   int G = 0;        // group padding, entries
@@ -1091,6 +1093,7 @@ extern "C" int mixdir_b200_last_timing(const mixdir_b200_handle* h, mixdir_b200_
 typedef void (*fused_fn)(FusedArgs);
 typedef void (*units_fn)(UnitArgs);
 typedef void (*seg_fn)(SegArgs);
+constexpr int kWsRegsE = 96, kWsRegsM = 32;  // k_em_seg_ws: registers per thread of the E-step / M-step warps
 static void layout_units(UnitPlan* up, int KC);
 
 static fused_fn pick_fused(int KC, int CB, int RG) {
@@ -1106,14 +1109,16 @@ static fused_fn pick_fused(int KC, int CB, int RG) {
 }
 
 static units_fn pick_units(int KC, int RG, int FPG, int W);
-static seg_fn pick_seg(int KC, int W, bool fs) {
+static seg_fn pick_seg(int KC, int W, bool fs, bool ws = false) {
+  if (KC == 16 && fs && ws) return k_em_seg_ws<kWsRegsE, kWsRegsM>;
   if (KC == 16 && fs) return k_em_seg<16, 512, true>;
   if (KC == 16) return k_em_seg<16, 512, false>;
   if (KC == 32) return W > 16 ? k_em_seg<32, 640, false> : k_em_seg<32, 512, false>;
   return nullptr;
 }
+static int plan_threads(const Plan& p) { return (p.engine == 5 && p.sp.ws) ? 1024 : 32 * p.W; }
 static const void* plan_fn(const mixdir_b200_handle* h, const Plan& p) {
-  if (p.engine == 5) return (const void*)pick_seg(p.KC, p.W, p.sp.fs);
+  if (p.engine == 5) return (const void*)pick_seg(p.KC, p.W, p.sp.fs, p.sp.ws);
   if (p.engine == 4) return (const void*)pick_units(p.KC, p.RG, p.FPG, p.W);
   return (const void*)pick_fused(p.KC, h->CB, p.RG);
 }
@@ -1139,7 +1144,7 @@ static int plan_occupancy(const mixdir_b200_handle* h, Shard& s, const Plan& p) 
     if (p.P > 1) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(p.P * s.sm_count);
-      cfg.blockDim = dim3(32 * p.W);
+      cfg.blockDim = dim3(plan_threads(p));
       cfg.dynamicSmemBytes = p.smem;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1151,7 +1156,7 @@ static int plan_occupancy(const mixdir_b200_handle* h, Shard& s, const Plan& p) 
       e = cudaOccupancyMaxActiveClusters(&nclus, fn, &cfg);
     } else {
       int nb = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 32 * p.W, p.smem);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, plan_threads(p), p.smem);
       nclus = nb * s.sm_count;
     }
   }
@@ -1507,7 +1512,10 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
      for (int gs = force_gs ? 1 : 0; gs <= (force_gs ? 1 : 0); gs++) {
       Plan c;
       const bool fs = KC == 16 && P == 2 && !getenv("MIXDIR_B200_NO_FEATURE_SPLIT");
-      layout_seg(h, R, fs ? 4 : 4 * RPW, fs, gs != 0, W, &c.sp);
+      // warp-specialised kernel (seg_ws.cuh): 16 M-step warps next to the W E-step warps
+      const bool ws = fs && !gs && W <= 15 && getenv("MIXDIR_B200_SEG_WS") != nullptr;
+      layout_seg(h, R, fs ? 4 : 4 * RPW, fs, gs != 0, ws ? 16 : W, &c.sp);
+      c.sp.ws = ws;
       const int maxSC = std::max(c.sp.SC[0], c.sp.SC[1]), maxJobs = std::max(c.sp.njobs[0], c.sp.njobs[1]);
       const int maxBlk = std::max(c.sp.blk_size[0], c.sp.blk_size[1]);
       UnitPlan up;
@@ -1790,7 +1798,7 @@ static int ensure_units(mixdir_b200_handle* h, Shard& s, const Plan& pl) {
   std::vector<UnitDesc> sig = up.desc;  // element order + what the placement depends on
   sig.push_back(UnitDesc{pl.engine, pl.KC, up.Q, up.srows});
   sig.push_back(UnitDesc{pl.R, pl.RG, pl.W, pl.FPG});
-  sig.push_back(UnitDesc{pl.sp.fs ? 1 : 0, pl.sp.G, pl.sp.TB, pl.sp.gs ? 1 : 0});
+  sig.push_back(UnitDesc{pl.sp.fs ? 1 : 0, pl.sp.G, pl.sp.TB, (pl.sp.gs ? 1 : 0) | (pl.sp.ws ? 2 : 0)});
   if (s.unit_valid && s.unit_sig.size() == sig.size() &&
       memcmp(s.unit_sig.data(), sig.data(), sig.size() * sizeof(UnitDesc)) == 0)
     return MIXDIR_B200_OK;
@@ -1971,7 +1979,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
       CU_TRY(ensure_smem_attr(s, plan_fn(h, pl), pl.smem));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(nclus * pl.P);
-      cfg.blockDim = dim3(32 * pl.W);
+      cfg.blockDim = dim3(plan_threads(pl));
       cfg.dynamicSmemBytes = pl.smem;
       cfg.stream = s.stream;
       cudaLaunchAttribute at[1];
@@ -2001,6 +2009,8 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
           g.sc0[o] = pl.sp.sc0[o]; g.SC[o] = pl.sp.SC[o];
         }
         g.gs = pl.sp.gs ? 1 : 0;
+        g.ws_we = pl.W;
+        g.ws_debug = getenv("MIXDIR_B200_WS_DEBUG") ? atoi(getenv("MIXDIR_B200_WS_DEBUG")) : 0;
         g.maxSC = std::max(pl.sp.SC[0], pl.sp.SC[1]);
         g.maxJobs = std::max(pl.sp.njobs[0], pl.sp.njobs[1]);
         g.maxBlk = std::max(pl.sp.blk_size[0], pl.sp.blk_size[1]);
@@ -2021,7 +2031,7 @@ static int launch_em(mixdir_b200_handle* h, Shard& s, int K, const Plan& pl, dou
         g.accumulate = chunked ? 1 : 0;
         g.bad = &s.d_scan->bad;
         g.stop = stop;
-        CU_TRY(cudaLaunchKernelEx(&cfg, pick_seg(pl.KC, pl.W, pl.sp.fs), g));
+        CU_TRY(cudaLaunchKernelEx(&cfg, pick_seg(pl.KC, pl.W, pl.sp.fs, pl.sp.ws), g));
       } else if (pl.engine == 4) {
         UnitArgs u;
         u.codes = a.codes;

@@ -103,6 +103,9 @@ struct SegArgs {
   int job0[2], njobs[2];
   int sc0[2], SC[2];
   int maxSC, maxJobs, maxBlk;  // shared-memory sizing (maxima over the owners)
+  int ws_we;                  // k_em_seg_ws (seg_ws.cuh): number of E-step warps = rows per tile / 16
+  int ws_debug;               // timing experiments only (results invalid): 1 = M warps skip their jobs,
+                              // 2 = E warps skip gather and soft-max
   int gs;                     // 1: no shared-memory statistics table (SC = 0); jobs[].w is the feature's
                               // first row of the GLOBAL table and every group sum is added there
   const int* eoff_rot;        // as k_em_units

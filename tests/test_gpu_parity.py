@@ -298,6 +298,33 @@ def test_seg_global_statistics_variant(monkeypatch):
         assert np.max(np.abs(a["class_prob"] - b["class_prob"])) < (CP_ATOL if K == 32 else 2e-5)
 
 
+def test_warp_specialised_seg_kernel_is_bit_identical(monkeypatch):
+    """MIXDIR_B200_SEG_WS=1 (A/B switch): k_em_seg_ws runs the E-step of tile t+1 on
+    15 warps with 96 registers next to the M-step of tile t on 16 warps with 32 (setmaxnreg), handing
+    the zeta tile over through cluster-wide mbarriers.  Same plan, same arithmetic, exact integer
+    statistics: every result must have the bits of the default kernel's; ragged row counts, NAs."""
+    pat = np.array([16, 12, 8, 4, 2, 10] * 10, dtype=np.int32)
+    K = 32
+    for N in (20_000, 100_003):
+        codes, _ = synth.make_codes(41, N, pat, K, p_na=0.04)
+        z0 = synth.zeta_init(41, min(N, 65536), K).sum(axis=0) * (N / min(N, 65536))
+        p0 = synth.phi_init(41, pat, K)
+        out = []
+        for ws in (False, True):
+            if ws:
+                monkeypatch.setenv("MIXDIR_B200_SEG_WS", "1")
+            else:
+                monkeypatch.delenv("MIXDIR_B200_SEG_WS", raising=False)
+            with Engine(codes, pat) as eng:
+                eng.set_engine(5)
+                out.append(eng.fit(K, z0, p0, max_iter=5, epsilon=-np.inf))
+        monkeypatch.delenv("MIXDIR_B200_SEG_WS", raising=False)
+        a, b = out
+        assert np.array_equal(a["phi"], b["phi"]) and np.array_equal(a["class_prob"], b["class_prob"])
+        assert np.array_equal(a["pred_class"], b["pred_class"])
+        assert rel(b["convergence"], a["convergence"]) < 1e-14  # (the entropy is an fp64 sum per CTA)
+
+
 def test_create_from_r_matrix_and_u16():
     ncat = np.array([300, 4, 7], dtype=np.int32)  # > 255 levels -> 2-byte codes
     codes, _ = synth.make_codes(9, 500, ncat, 4, p_na=0.1)
