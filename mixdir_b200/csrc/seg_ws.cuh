@@ -273,67 +273,57 @@ __global__ void __launch_bounds__(1024, 1) k_em_seg_ws(SegArgs a) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RM));
     // =========================== M-step warps ===========================
     const int mw = warp - MW;
-    const uint32_t zbase = smem_u32(z_s) + lane * 4;
+    const int half = lane >> 4, c2 = lane & 15;  // two classes per lane, the half-warps on different rows (seg.cuh)
+    const uint32_t zb2 = smem_u32(z_s) + c2 * 8;
+    const uint32_t selA = half ? 0x4441u : 0x4440u, selB = half ? 0x4443u : 0x4442u;
     const uint32_t seg_addr = smem_u32(seg_s);
     int it = 0;
     for (int t = cluster_id; t < a.n_tiles; t += n_clusters, ++it) {
       const uint32_t par = (uint32_t)(it & 1);
       mbar_wait(&bar[1], par);
       mbar_wait_cluster(zfull, par);
+      if (a.ws_debug & 8) {  // timing experiment: an M-step that only takes time (no instructions, no loads)
+        const long long t0 = clock64();
+        while (clock64() - t0 < 14000) __nanosleep(500);
+      }
       for (int job = mw; job < ((a.ws_debug & 1) ? 0 : a.njobs[own]); job += MW) {
         const int4 jd = jobs_s[job];
         const int C = jd.z & 0xff;
         uint32_t p = seg_addr + (uint32_t)jd.x;
         const uint32_t* cnt = reinterpret_cast<const uint32_t*>(seg_s + jd.y);  // 4-byte aligned
-        unsigned long long* srow = S_s + (size_t)jd.w * SW + lane;
+        ulonglong2* srow = reinterpret_cast<ulonglong2*>(S_s + (size_t)jd.w * SW) + c2;
         uint32_t w = lds_u32(p);
         uint32_t cw = 0;
-        for (int c = 0; c < C; c++, srow += SW) {
+        for (int c = 0; c < C; c++, srow += SW / 2) {
           if ((c & 3) == 0) cw = cnt[c >> 2];  // group sizes of four codes at a time
           const int n = (int)((cw >> (8 * (c & 3))) & 0xffu);
           if (n == 0) continue;  // warp-uniform
-          const unsigned long long old = *srow;
-          unsigned long long s0 = 0ull, s1 = 0ull;
+          const ulonglong2 old = *srow;
+          unsigned long long sa = 0ull, sb = 0ull;
           int g = 0;
-          if (a.ws_debug & 4) {  // timing experiment: the same loop without the zeta loads
-            for (; g + 2 <= n; g += 2) {
-              const uint32_t w1 = lds_u32(p + 4);
-              p += 8;
-              const uint32_t wn = lds_u32(p);
-              s0 += __byte_perm(w, 0u, 0x4440u) * ZS; s1 += __byte_perm(w, 0u, 0x4441u) * ZS;
-              s0 += __byte_perm(w, 0u, 0x4442u) * ZS; s1 += __byte_perm(w, 0u, 0x4443u) * ZS;
-              s0 += __byte_perm(w1, 0u, 0x4440u) * ZS; s1 += __byte_perm(w1, 0u, 0x4441u) * ZS;
-              s0 += __byte_perm(w1, 0u, 0x4442u) * ZS; s1 += __byte_perm(w1, 0u, 0x4443u) * ZS;
-              w = wn;
-            }
-          }
           for (; g + 2 <= n; g += 2) {
             const uint32_t w1 = lds_u32(p + 4);
             p += 8;
             const uint32_t wn = lds_u32(p);
-            const uint32_t z0 = lds_u32(zbase + __byte_perm(w, 0u, 0x4440u) * ZS);
-            const uint32_t z1 = lds_u32(zbase + __byte_perm(w, 0u, 0x4441u) * ZS);
-            const uint32_t z2 = lds_u32(zbase + __byte_perm(w, 0u, 0x4442u) * ZS);
-            const uint32_t z3 = lds_u32(zbase + __byte_perm(w, 0u, 0x4443u) * ZS);
-            const uint32_t z4 = lds_u32(zbase + __byte_perm(w1, 0u, 0x4440u) * ZS);
-            const uint32_t z5 = lds_u32(zbase + __byte_perm(w1, 0u, 0x4441u) * ZS);
-            const uint32_t z6 = lds_u32(zbase + __byte_perm(w1, 0u, 0x4442u) * ZS);
-            const uint32_t z7 = lds_u32(zbase + __byte_perm(w1, 0u, 0x4443u) * ZS);
-            s0 += z0; s1 += z1; s0 += z2; s1 += z3;
-            s0 += z4; s1 += z5; s0 += z6; s1 += z7;
+            const uint2 z0 = lds_u32x2(zb2 + __byte_perm(w, 0u, selA) * ZS);
+            const uint2 z1 = lds_u32x2(zb2 + __byte_perm(w, 0u, selB) * ZS);
+            const uint2 z2 = lds_u32x2(zb2 + __byte_perm(w1, 0u, selA) * ZS);
+            const uint2 z3 = lds_u32x2(zb2 + __byte_perm(w1, 0u, selB) * ZS);
+            sa += z0.x; sb += z0.y; sa += z1.x; sb += z1.y;
+            sa += z2.x; sb += z2.y; sa += z3.x; sb += z3.y;
             w = wn;
           }
           if (g < n) {
             p += 4;
             const uint32_t wn = lds_u32(p);
-            const uint32_t z0 = lds_u32(zbase + __byte_perm(w, 0u, 0x4440u) * ZS);
-            const uint32_t z1 = lds_u32(zbase + __byte_perm(w, 0u, 0x4441u) * ZS);
-            const uint32_t z2 = lds_u32(zbase + __byte_perm(w, 0u, 0x4442u) * ZS);
-            const uint32_t z3 = lds_u32(zbase + __byte_perm(w, 0u, 0x4443u) * ZS);
-            s0 += z0; s1 += z1; s0 += z2; s1 += z3;
+            const uint2 z0 = lds_u32x2(zb2 + __byte_perm(w, 0u, selA) * ZS);
+            const uint2 z1 = lds_u32x2(zb2 + __byte_perm(w, 0u, selB) * ZS);
+            sa += z0.x; sb += z0.y; sa += z1.x; sb += z1.y;
             w = wn;
           }
-          *srow = old + (s0 + s1);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+          if (half == 0) *srow = make_ulonglong2(old.x + sa, old.y + sb);
         }
       }
       // this warp has left the zeta tile (both CTAs' E warps wait for it) and the segment lists
