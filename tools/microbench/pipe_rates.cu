@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, double* out, long long* 
 #pragma unroll
   for (int i = 0; i < 8; i++) s += d[i] + u[i] + (double)q[i] + f[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+  // the slowest warp of the block (in the mixed modes the two kinds of warps may finish apart)
+  atomicMax((unsigned long long*)&cyc[blockIdx.x], (unsigned long long)(t1 - t0));
+  if (lane == 0 && (MODE == 5 || MODE == 6)) atomicMax((unsigned long long*)&cyc[148 + blockIdx.x * 2 + (fp ? 0 : 1)], (unsigned long long)(t1 - t0));
 }
 
 template <int MODE>
@@ -91,19 +93,23 @@ void run(const char* name, double per_iter_class_instr /* warp instructions of t
   double* out;
   long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 8);
-  cudaMalloc(&cyc, 148 * 8);
+  cudaMalloc(&cyc, 148 * 3 * 8);
   for (int warps : {8, 16, 32}) {
     const int iters = 2000;
     k<MODE><<<148, warps * 32>>>(10, out, cyc);
+    cudaMemset(cyc, 0, 148 * 3 * 8);
     k<MODE><<<148, warps * 32>>>(iters, out, cyc);
     cudaDeviceSynchronize();
-    long long h[148];
+    long long h[148 * 3];
     cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-    double avg = 0;
-    for (int i = 0; i < 148; i++) avg += h[i];
-    avg /= 148;
+    double avg = 0, a0 = 0, a1 = 0;
+    for (int i = 0; i < 148; i++) { avg += h[i]; a0 += h[148 + 2 * i]; a1 += h[148 + 2 * i + 1]; }
+    avg /= 148; a0 /= 148; a1 /= 148;
     const double n = (double)iters * per_iter_class_instr * warps * frac_warps;
-    printf("%-58s warps=%2d  %.3f cycles per warp instruction per SM\n", name, warps, avg / n);
+    if (MODE == 5 || MODE == 6)
+      printf("%-58s warps=%2d  fp64 warps done after %.3f, the other warps after %.3f cycles per instruction of their kind per SM\n", name, warps, a0 / n, a1 / n);
+    else
+      printf("%-58s warps=%2d  %.3f cycles per warp instruction per SM\n", name, warps, avg / n);
   }
   cudaFree(out);
   cudaFree(cyc);
