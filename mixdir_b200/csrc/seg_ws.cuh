@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(1024, 1) k_em_seg_ws(SegArgs a) {
       const int wrow0 = warp * RW;
       const int row_in_tile0 = wrow0 + slot * RG;
       const unsigned slot_mask = ((1u << KC) - 1u) << (slot * KC);
-      const int rot = slot & 3;
+      // No element rotation here (units.cuh rotates the elements of a code word per slot to spread 64-byte
+      // table rows over the banks; with 16 or 32 classes per CTA a table row is a whole 128-byte line): every
+      // row adds its logit terms in the SAME order wherever it sits in a tile, so the responsibilities -- and
+      // with the integer statistics the whole fit -- do not depend on where a shard starts.
+      constexpr int rot = 0;
       const int4* ro_mine = reinterpret_cast<const int4*>(ro_s + rot * U);
 
       int it = 0;

@@ -15,17 +15,19 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("engine", [0, 4], ids=["auto_seg", "units_fp64"])
+@pytest.mark.parametrize("engine,K", [(0, 20), (0, 32), (4, 20)], ids=["auto_seg_k20", "auto_seg_k32", "units_fp64"])
 @pytest.mark.parametrize("dp", [False, True])
-def test_single_process_two_devices_match_one(dp, engine):
+def test_single_process_two_devices_match_one(dp, engine, K):
     """engine 0 picks the sorted-segment kernel here (>= 16,384 rows): its statistics AND class masses
     are exact integer sums, so the whole trajectory (phi, class_prob) must come out BIT-identical on
     one and on two devices; only the ELBO (fp64 entropy sum) may differ in the last bits.  The fp64
-    kernel (engine 4) re-associates its sums across shards."""
+    kernel (engine 4) re-associates its sums across shards.  (K = 32 runs two CTAs of 16 classes with two
+    rows per warp instruction; the second shard starts at row 25,000 = 8 mod 16, so its rows sit in the
+    other half-warp than on one device: the logit sums must not depend on that.)"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     pat = np.array([16, 12, 8, 4, 2, 10] * 5, dtype=np.int32)
-    N, K = 50_001, 20
+    N = 50_001
     codes, _ = synth.make_codes(5, N, pat, K, p_na=0.05)
     z0 = synth.zeta_init(5, N, K)
     p0 = synth.phi_init(5, pat, K)
