@@ -19,21 +19,26 @@
 // code) instead of once per row.  Per (row, feature, class) that moves 4 bytes:
 //
 //   * zeta enters the M-step as 32-bit FIXED POINT, floor(zeta * (2^32 - 1) + u) with u in [0, 1) a
-//     hash of (row, class) -- stochastic, i.e. UNBIASED rounding -- and all sums are 64-bit INTEGERS:
-//     exact and order-independent, so the phi statistics are bit-identical whatever the tile order
-//     or grid size (SURVEY 8e recommends exactly this).  Stated precision of the per-row math:
-//     logits, soft-max, entropy and the class masses colSums(zeta) (they order the classes of the DP
-//     variant and enter omega/kappa/lambda) in fp64 as before; the responsibilities that feed phi
-//     carry zero-mean noise of 2^-32 per entry.  (Round-to-nearest was measured first: it sends
-//     every responsibility below half a unit to 0, a one-sided error that enters the ELBO's data
-//     term weighted with logits of -25 .. -100: 5e-9 .. 9e-9 relative at K = 32 whatever the number
-//     of rows.)  What remains is noise of ~1e-11 .. 1e-10 of the ELBO that the coordinate ascent
-//     itself amplifies while classes merge (profiles/r02_seg_precision.txt);
-//     the automatic engine choice takes this kernel only from 16384 rows on, and
+//     32-bit mix of (global row, class) -- stochastic, i.e. UNBIASED rounding -- and all sums are
+//     64-bit INTEGERS: exact and order-independent (SURVEY 8e recommends exactly this).  The class
+//     masses colSums(zeta) (they order the classes of the DP variant and enter omega / kappa / lambda)
+//     keep full precision as two-word integers (cs_value below).  Per row, logits, soft-max and entropy
+//     are fp64, and every row adds its logit terms in the same order wherever it sits in a tile.
+//     Together: everything that feeds the next iteration is the same whatever the tile order, the grid
+//     size, the number of GPUs or the place where a shard starts -- fits are bit-identical on 1 and N
+//     GPUs (only the entropy term of the ELBO is an fp64 sum).  Stated precision: the responsibilities
+//     that feed phi carry zero-mean noise of 2^-32 per entry.  (Round-to-nearest was measured first:
+//     it sends every responsibility below half a unit to 0, a one-sided error that enters the ELBO's
+//     data term weighted with logits of -25 .. -100: 5e-9 .. 9e-9 relative at K = 32 whatever the
+//     number of rows.)  What remains is noise of ~1e-11 .. 1e-10 of the ELBO that the coordinate
+//     ascent itself amplifies while classes merge (profiles/r02_seg_precision.txt, DESIGN.md section
+//     5); the automatic engine choice takes this kernel only from 16384 rows on, and
 //     mixdir_b200_set_engine(h, 4) selects fp64 statistics.
 //   * no partial buffers and no reduction kernel: every CTA adds its histogram slice to the global
 //     int64 statistics with RED.ADD.U64; the last CTA to finish (atomic ticket) sums the per-CTA
 //     entropy partials in index order and writes the tail of the statistics buffer.
+//   * M-step of the feature split: a lane takes two classes (one 64-bit load), the half-warps take
+//     different rows of a list word -- 2.6 instructions per (row, feature).
 //
 //   * FEATURE SPLIT (FS, clusters of two CTAs with 16 classes each, i.e. K = 17..32): the E-step
 //     splits the CLASSES over the cluster as before, but the M-step splits the FEATURES: every CTA
