@@ -367,46 +367,62 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
     } else {
       __syncwarp();
     }
-    double M_o = -INFINITY, f_o = 0.0, logs_o = 0.0;
+    // per-row scalar, once per row by an owner lane: f = exp(m_own - M) / sum, so that zeta = e * f.
+    // Entropy of a row (R/mixdir_vi.R:181-184): -sum_k zeta_k log zeta_k with log zeta_k = l_k - c,
+    // c = M + log(sum), i.e. c * sum_k zeta_k - sum_k zeta_k l_k = c - sum_k zeta_k l_k: the owner lane adds
+    // c once per row (the log stays off the path the other lanes wait on), every lane its zeta_k l_k.
+    double f_o = 0.0;
     if (lane < RW) {
       double2* mine_p = ex + wrow0 + lane;
-      double2 v[8];
-#pragma unroll
-      for (int p = 0; p < 8; p++) {
-        v[p] = make_double2(-INFINITY, -0.0);
-        if (p < P) v[p] = (P > 1 && p != rank) ? *cluster.map_shared_rank(mine_p, p) : *mine_p;
-      }
-      double M = -INFINITY;
       bool live = false;
+      double M = -INFINITY, stot = 0.0, e_mine = 0.0;
+      if constexpr (FS) {
+        // two CTAs: one of the two weights exp(m - M) is exp(0) = 1 exactly, so ONE exp is enough (the
+        // general path below evaluates three, one after the other, while the whole warp waits)
+        const double2 v0 = *mine_p, v1 = *cluster.map_shared_rank(mine_p, rank ^ 1);
+        M = fmax(v0.x, v1.x);
+        live = !signbit(v0.y) || !signbit(v1.y);
+        const bool own_max = v0.x >= v1.x;
+        const double eo = exp_nonpos((own_max ? v1.x : v0.x) - M);
+        const double e0 = own_max ? 1.0 : eo, e1 = own_max ? eo : 1.0;
+        const double t0 = (v0.x != -INFINITY) ? fabs(v0.y) * e0 : 0.0;
+        const double t1 = (v1.x != -INFINITY) ? fabs(v1.y) * e1 : 0.0;
+        stot = rank == 0 ? t0 + t1 : t1 + t0;  // rank order, as the general path
+        e_mine = (v0.x == -INFINITY) ? 0.0 : e0;
+      } else {
+        double2 v[8];
 #pragma unroll
-      for (int p = 0; p < 8; p++) {
-        if (p < P) {
-          M = fmax(M, v[p].x);
-          live = live || !signbit(v[p].y);
+        for (int p = 0; p < 8; p++) {
+          v[p] = make_double2(-INFINITY, -0.0);
+          if (p < P) v[p] = (P > 1 && p != rank) ? *cluster.map_shared_rank(mine_p, p) : *mine_p;
         }
-      }
-      double stot = 0.0;
 #pragma unroll
-      for (int p = 0; p < 8; p++)
-        if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp_nonpos(v[p].x - M);
-      const double mine = mine_p->x;
-      f_o = (mine == -INFINITY) ? 0.0 : exp_nonpos(mine - M) / stot;
-      logs_o = log(stot);
-      M_o = M;
+        for (int p = 0; p < 8; p++) {
+          if (p < P) {
+            M = fmax(M, v[p].x);
+            live = live || !signbit(v[p].y);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+          if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp_nonpos(v[p].x - M);
+        const double mine = mine_p->x;
+        e_mine = (mine == -INFINITY) ? 0.0 : exp_nonpos(mine - M);
+      }
+      f_o = e_mine / stot;
       const bool valid = (int64_t)t * R + wrow0 + lane < a.n_rows;
       if (valid && !live) uflag = 1;
+      if (valid && rank == 0) hacc += M + log(stot);  // (one CTA of the cluster counts the row's c)
     }
 #pragma unroll
     for (int rg = 0; rg < RG; rg++) {
       const int src = slot * RG + rg;
-      const double M = __shfl_sync(0xffffffffu, M_o, src);
       const double f = __shfl_sync(0xffffffffu, f_o, src);
-      const double logs = __shfl_sync(0xffffffffu, logs_o, src);
       const bool valid = (int64_t)t * R + row_in_tile0 + rg < a.n_rows;
       double zz = 0.0;
       if (valid && kreal) {
         zz = ez[rg] * f;  // zeta / rowSums(zeta)
-        hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - logs) : kTiny;  // R/mixdir_vi.R:181-184
+        hacc -= (zz > DBL_MIN) ? zz * lg[rg] : kTiny;  // (responsibilities below xmin count as xmin, as in R)
       }
       zz = (zz > 0.0) ? zz : 0.0;  // NaN (an underflowing row: the pass is discarded) -> 0
       {  // class mass: two-word integer (cs_value)

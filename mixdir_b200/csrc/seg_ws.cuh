@@ -199,39 +199,39 @@ __global__ void __launch_bounds__(1024, 1) k_em_seg_ws(SegArgs a) {
           if (kc == 0) ex[row_in_tile0 + rg] = make_double2(m, live ? s : -s);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&xbar[warp], (uint32_t)(rank ^ 1));
-        mbar_wait_cluster(&xbar[warp], par);
+        if (!(a.ws_debug & 16)) {  // (16: timing experiment without the exchange across the cluster)
+          if (lane == 0) mbar_arrive_remote(&xbar[warp], (uint32_t)(rank ^ 1));
+          mbar_wait_cluster(&xbar[warp], par);
+        }
 
-        double M_o = -INFINITY, f_o = 0.0, logs_o = 0.0;
+        double f_o = 0.0;  // per-row scalar (seg.cuh): exp(m_own - M) / sum; the owner lane adds the row's c
         if (lane < RW) {
           double2* mine_p = ex + wrow0 + lane;
           const double2 v0 = *mine_p;
-          const double2 v1 = *cluster.map_shared_rank(mine_p, rank ^ 1);
+          const double2 v1 = (a.ws_debug & 16) ? v0 : *cluster.map_shared_rank(mine_p, rank ^ 1);
           const double M = fmax(v0.x, v1.x);
           const bool live = !signbit(v0.y) || !signbit(v1.y);
-          double stot = 0.0;
-          // (rank order, as k_em_seg: p = 0 first)
-          const double2 va = rank == 0 ? v0 : v1, vb = rank == 0 ? v1 : v0;
-          if (va.x != -INFINITY) stot += fabs(va.y) * exp_nonpos(va.x - M);
-          if (vb.x != -INFINITY) stot += fabs(vb.y) * exp_nonpos(vb.x - M);
-          f_o = (v0.x == -INFINITY) ? 0.0 : exp_nonpos(v0.x - M) / stot;
-          logs_o = log(stot);
-          M_o = M;
+          const bool own_max = v0.x >= v1.x;
+          const double eo = exp_nonpos((own_max ? v1.x : v0.x) - M);
+          const double e0 = own_max ? 1.0 : eo, e1 = own_max ? eo : 1.0;
+          const double t0 = (v0.x != -INFINITY) ? fabs(v0.y) * e0 : 0.0;
+          const double t1 = (v1.x != -INFINITY) ? fabs(v1.y) * e1 : 0.0;
+          const double stot = rank == 0 ? t0 + t1 : t1 + t0;
+          f_o = ((v0.x == -INFINITY) ? 0.0 : e0) / stot;
           const bool valid = (int64_t)t * R + wrow0 + lane < a.n_rows;
           if (valid && !live) uflag = 1;
+          if (valid && rank == 0) hacc += M + log(stot);
         }
         uint32_t zf[RG];
 #pragma unroll
         for (int rg = 0; rg < RG; rg++) {
           const int src = slot * RG + rg;
-          const double M = __shfl_sync(0xffffffffu, M_o, src);
           const double f = __shfl_sync(0xffffffffu, f_o, src);
-          const double logs = __shfl_sync(0xffffffffu, logs_o, src);
           const bool valid = (int64_t)t * R + row_in_tile0 + rg < a.n_rows;
           double zz = 0.0;
           if (valid && kreal) {
             zz = ez[rg] * f;  // zeta / rowSums(zeta)
-            hacc -= (zz > DBL_MIN) ? zz * ((lg[rg] - M) - logs) : kTiny;  // R/mixdir_vi.R:181-184
+            hacc -= (zz > DBL_MIN) ? zz * lg[rg] : kTiny;  // R/mixdir_vi.R:181-184
           }
           zz = (zz > 0.0) ? zz : 0.0;
           {
@@ -247,12 +247,15 @@ __global__ void __launch_bounds__(1024, 1) k_em_seg_ws(SegArgs a) {
 #pragma unroll
         for (int rg = 0; rg < RG; rg++) {
           z_s[(row_in_tile0 + rg) * 32 + kg] = zf[rg];
-          z_peer[(row_in_tile0 + rg) * 32 + kg] = zf[rg];
+          if (!(a.ws_debug & 32)) z_peer[(row_in_tile0 + rg) * 32 + kg] = zf[rg];
         }
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_local_cluster(zfull);
-          mbar_arrive_remote(zfull, (uint32_t)(rank ^ 1));
+          if (a.ws_debug & 32)  // (32: timing experiment without the remote half of the zeta tile)
+            mbar_arrive_local_cluster(zfull);
+          else
+            mbar_arrive_remote(zfull, (uint32_t)(rank ^ 1));
         }
       }
     } else if (warp == MW - 1) {
@@ -334,7 +337,10 @@ __global__ void __launch_bounds__(1024, 1) k_em_seg_ws(SegArgs a) {
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_local_cluster(zfree);
-        mbar_arrive_remote(zfree, (uint32_t)(rank ^ 1));
+        if (a.ws_debug & 32)
+          mbar_arrive_local_cluster(zfree);
+        else
+          mbar_arrive_remote(zfree, (uint32_t)(rank ^ 1));
         mbar_arrive_cta(seg_free);
       }
     }
