@@ -396,18 +396,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
           v[p] = make_double2(-INFINITY, -0.0);
           if (p < P) v[p] = (P > 1 && p != rank) ? *cluster.map_shared_rank(mine_p, p) : *mine_p;
         }
-#pragma unroll
-        for (int p = 0; p < 8; p++) {
-          if (p < P) {
-            M = fmax(M, v[p].x);
-            live = live || !signbit(v[p].y);
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < 8; p++)
-          if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp_nonpos(v[p].x - M);
-        const double mine = mine_p->x;
-        e_mine = (mine == -INFINITY) ? 0.0 : exp_nonpos(mine - M);
+        row_scalars(v, P, rank, M, live, stot, e_mine);  // (units.cuh)
       }
       f_o = e_mine / stot;
       const bool valid = (int64_t)t * R + wrow0 + lane < a.n_rows;

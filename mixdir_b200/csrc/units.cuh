@@ -97,6 +97,51 @@ __device__ __forceinline__ void load_code_words(const uint32_t* p, uint32_t* out
   }
 }
 
+// Row-level soft-max scalars from the (max, sum) pairs of the P CTAs of a cluster (owner lanes, once per
+// row): M = largest maximum, stot = sum_p |s_p| exp(m_p - M) in rank order, e_mine = exp(m_own - M).
+// This section runs on every warp of the CTA at the same moment with nothing to overlap it, so its
+// dependent fp64 chains count: one CTA needs no exp at all (exp(0) = 1 exactly), two need one (the
+// larger maximum has weight 1), and for more the exps are evaluated side by side, not one after the
+// other.  Same bits as the plain loop  stot += |s_p| * exp(m_p - M).
+__device__ __forceinline__ void row_scalars(const double2 (&v)[8], int P, int rank, double& M, bool& live,
+                                            double& stot, double& e_mine) {
+  M = -INFINITY;
+  live = false;
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    if (p < P) {
+      M = fmax(M, v[p].x);
+      live = live || !signbit(v[p].y);
+    }
+  }
+  if (P == 1) {
+    const bool on = v[0].x != -INFINITY;
+    stot = on ? fabs(v[0].y) : 0.0;
+    e_mine = on ? 1.0 : 0.0;
+  } else if (P == 2) {
+    const bool first_max = v[0].x >= v[1].x;
+    const double eo = exp_nonpos((first_max ? v[1].x : v[0].x) - M);
+    const double e0 = first_max ? 1.0 : eo, e1 = first_max ? eo : 1.0;
+    const double t0 = (v[0].x != -INFINITY) ? fabs(v[0].y) * e0 : 0.0;
+    const double t1 = (v[1].x != -INFINITY) ? fabs(v[1].y) * e1 : 0.0;
+    stot = t0 + t1;
+    e_mine = rank == 0 ? ((v[0].x == -INFINITY) ? 0.0 : e0) : ((v[1].x == -INFINITY) ? 0.0 : e1);
+  } else {
+    double e[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) e[p] = exp_nonpos(v[p].x - M);  // (p >= P: -inf -> 0)
+    stot = 0.0;
+    e_mine = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+      if (p < P && v[p].x != -INFINITY) {
+        stot += fabs(v[p].y) * e[p];
+        if (p == rank) e_mine = e[p];
+      }
+    }
+  }
+}
+
 // MAXT: launch bound in threads.  512 (16 warps) leaves the compiler 128 registers; 640 (20 warps,
 // <= 102 registers) is used when the tiles of 20 warps fit next to the tables.
 template <int KC, int RG, int FPG, int MAXT>
@@ -271,21 +316,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_units(UnitArgs a) {
         v[p] = make_double2(-INFINITY, -0.0);
         if (p < P) v[p] = (P > 1 && p != rank) ? *cluster.map_shared_rank(mine_p, p) : *mine_p;
       }
-      double M = -INFINITY;
-      bool live = false;
-#pragma unroll
-      for (int p = 0; p < 8; p++) {
-        if (p < P) {
-          M = fmax(M, v[p].x);
-          live = live || !signbit(v[p].y);
-        }
-      }
-      double stot = 0.0;
-#pragma unroll
-      for (int p = 0; p < 8; p++)
-        if (p < P && v[p].x != -INFINITY) stot += fabs(v[p].y) * exp_nonpos(v[p].x - M);
-      const double mine = mine_p->x;
-      f_o = (mine == -INFINITY) ? 0.0 : exp_nonpos(mine - M) / stot;
+      double M, stot, e_mine;
+      bool live;
+      row_scalars(v, P, rank, M, live, stot, e_mine);
+      f_o = e_mine / stot;
       logs_o = log(stot);
       M_o = M;
       const bool valid = (int64_t)t * R + wrow0 + lane < a.n_rows;
