@@ -181,6 +181,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   } while (!done);
 }
 
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // read-only during the M-step (written before the barrier that opens it): the compiler may schedule freely
 __device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
   uint2 v;
@@ -244,8 +247,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);  // code tile
     mbar_init(&bar[1], 1);  // segment lists
-    if (FS)
+    if (FS) {
       for (int w = 0; w < W; w++) mbar_init(&xbar[w], 1);  // one arrival per tile: the peer's warp w
+      mbar_init(&xbar[24], W);                             // "M-step of the tile done": one arrival per warp
+      *reinterpret_cast<int*>(&xbar[25]) = 0;              // ... and a count: the last warp refills the lists
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -360,6 +366,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       // warps drift apart and gather, soft-max arithmetic and exchange latency overlap.  (The
       // cluster barrier below, once per tile, keeps the two CTAs within one phase of each other.)
       __syncwarp();
+      // No block barrier closes the M-step of the previous tile (below): before this warp tells the peer
+      // "my pairs are written", every warp of THIS CTA must have left the previous zeta tile -- the peer
+      // takes the arrival as leave to write into it.  By now that wait is over almost always.
+      if (it > 0) mbar_wait(&xbar[24], (uint32_t)((it - 1) & 1));
       if (lane == 0) mbar_arrive_remote(&xbar[warp], (uint32_t)(rank ^ 1));
       mbar_wait_cluster(&xbar[warp], par);
     } else if (P > 1) {
@@ -547,16 +557,35 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
         }
       }
     }
-    __syncthreads();  // zeta tile and segment lists may be overwritten
-
-    if (threadIdx.x == 0 && t + n_clusters < a.n_tiles) {
-      mbar_expect_tx(&bar[1], (uint32_t)a.blk_size[own]);
-      tma_load_1d(seg_s, a.seg + (size_t)(t + n_clusters) * a.TB + a.blk_off[own],
-                  (uint32_t)a.blk_size[own], &bar[1]);
+    if (FS) {
+      // split-phase end of the M-step: a warp arrives and goes on to the next tile's gather; whoever
+      // arrives last refills the segment lists (the waits are in the E-step, see above)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cta(&xbar[24]);
+        int* cnt_done = reinterpret_cast<int*>(&xbar[25]);
+        if (atomicAdd(cnt_done, 1) == W - 1) {
+          *cnt_done = 0;
+          if (t + n_clusters < a.n_tiles) {
+            mbar_expect_tx(&bar[1], (uint32_t)a.blk_size[own]);
+            tma_load_1d(seg_s, a.seg + (size_t)(t + n_clusters) * a.TB + a.blk_off[own],
+                        (uint32_t)a.blk_size[own], &bar[1]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      __syncthreads();  // zeta tile and segment lists may be overwritten
+      if (threadIdx.x == 0 && t + n_clusters < a.n_tiles) {
+        mbar_expect_tx(&bar[1], (uint32_t)a.blk_size[own]);
+        tma_load_1d(seg_s, a.seg + (size_t)(t + n_clusters) * a.TB + a.blk_off[own],
+                    (uint32_t)a.blk_size[own], &bar[1]);
+      }
     }
   }
 
   // ---- flush: integer adds into the global statistics; last CTA writes the tail ----
+  __syncthreads();  // (the feature-split loop ends without a block barrier)
   {
     {  // (the row map is read in batches of eight: one global-load latency per batch, not per entry)
       const int n = a.SC[own] * SW, step = blockDim.x;

@@ -26,9 +26,6 @@
 
 namespace mxd {
 
-__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // arrive on a barrier of THIS CTA, releasing at cluster scope (the waiters may be fed by the peer too)
 __device__ __forceinline__ void mbar_arrive_local_cluster(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
