@@ -247,11 +247,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);  // code tile
     mbar_init(&bar[1], 1);  // segment lists
-    if (FS) {
+    if (FS)
       for (int w = 0; w < W; w++) mbar_init(&xbar[w], 1);  // one arrival per tile: the peer's warp w
-      mbar_init(&xbar[24], W);                             // "M-step of the tile done": one arrival per warp
-      *reinterpret_cast<int*>(&xbar[25]) = 0;              // ... and a count: the last warp refills the lists
-    }
+    mbar_init(&xbar[24], W);                               // "M-step of the tile done": one arrival per warp
+    *reinterpret_cast<int*>(&xbar[25]) = 0;                // ... and a count: the last warp refills the lists
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -413,6 +412,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
       if (valid && !live) uflag = 1;
       if (valid && rank == 0) hacc += M + log(stot);  // (one CTA of the cluster counts the row's c)
     }
+    // (without the feature split the zeta tile is this CTA's own: before the first store below every
+    // warp of the CTA must have left the previous tile's M-step -- see the end of the M-step)
+    if (!FS && it > 0) mbar_wait(&xbar[24], (uint32_t)((it - 1) & 1));
 #pragma unroll
     for (int rg = 0; rg < RG; rg++) {
       const int src = slot * RG + rg;
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
         }
       }
     }
-    if (FS) {
+    {
       // split-phase end of the M-step: a warp arrives and goes on to the next tile's gather; whoever
       // arrives last refills the segment lists (the waits are in the E-step, see above)
       __syncwarp();
@@ -574,13 +576,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
         }
       }
       __syncwarp();
-    } else {
-      __syncthreads();  // zeta tile and segment lists may be overwritten
-      if (threadIdx.x == 0 && t + n_clusters < a.n_tiles) {
-        mbar_expect_tx(&bar[1], (uint32_t)a.blk_size[own]);
-        tma_load_1d(seg_s, a.seg + (size_t)(t + n_clusters) * a.TB + a.blk_off[own],
-                    (uint32_t)a.blk_size[own], &bar[1]);
-      }
     }
   }
 
