@@ -478,25 +478,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_em_seg(SegArgs a) {
           if (n == 0) continue;  // warp-uniform
           const ulonglong2 old = *srow;  // early: its latency hides behind the loop
           unsigned long long sa = 0ull, sb = 0ull;
-          int g = 0;
-          for (; g + 2 <= n; g += 2) {  // two list words (8 rows) per round
-            const uint32_t w1 = lds_u32(p + 4);
-            p += 8;
-            const uint32_t wn = lds_u32(p);  // next list word (one word of slack behind the lists)
+          // two list words (8 rows) per round; an odd last word is paired with four dummy rows (zero
+          // responsibilities), so the loop has no tail block
+          for (int g = 0; g < n; g += 2) {
+            const bool two = g + 1 < n;
+            const uint32_t w1r = lds_u32(p + 4);  // (one word of slack behind the lists)
+            const uint32_t w1 = two ? w1r : 0xffffffffu;
+            p += two ? 8 : 4;
+            const uint32_t wn = two ? lds_u32(p) : w1r;  // next list word
             const uint2 z0 = lds_u32x2(zb2 + __byte_perm(w, 0u, selA) * ZS);
             const uint2 z1 = lds_u32x2(zb2 + __byte_perm(w, 0u, selB) * ZS);
             const uint2 z2 = lds_u32x2(zb2 + __byte_perm(w1, 0u, selA) * ZS);
             const uint2 z3 = lds_u32x2(zb2 + __byte_perm(w1, 0u, selB) * ZS);
             sa += z0.x; sb += z0.y; sa += z1.x; sb += z1.y;
             sa += z2.x; sb += z2.y; sa += z3.x; sb += z3.y;
-            w = wn;
-          }
-          if (g < n) {
-            p += 4;
-            const uint32_t wn = lds_u32(p);
-            const uint2 z0 = lds_u32x2(zb2 + __byte_perm(w, 0u, selA) * ZS);
-            const uint2 z1 = lds_u32x2(zb2 + __byte_perm(w, 0u, selB) * ZS);
-            sa += z0.x; sb += z0.y; sa += z1.x; sb += z1.y;
             w = wn;
           }
           sa += __shfl_xor_sync(0xffffffffu, sa, 16);
