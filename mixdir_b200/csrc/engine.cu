@@ -278,6 +278,7 @@ struct mixdir_b200_handle {
   std::vector<uint8_t> has_na;   // [J] 0: the feature holds no NA anywhere (valid once scan_resolved)
   std::vector<Shard> shards;
   int rank = 0, world = 1;   // multi-process flavour
+  int64_t n_rows_global = 0; // rows of all ranks together (multi-process flavour; else = n_rows)
   int64_t row_offset = 0;    // global number of this rank's first row (seeds k_em_seg's rounding hash:
                              // the same rows get the same rounding whatever the number of ranks)
   int engine_pref = 0;
@@ -971,6 +972,8 @@ static int exchange_row_offset(mixdir_b200_handle* h) {
   CU_TRY(cudaStreamSynchronize(s.stream));
   dfree(d);
   h->row_offset = 0;
+  h->n_rows_global = 0;
+  for (int r = 0; r < h->world; r++) h->n_rows_global += cnt[r];
   for (int r = 0; r < h->rank; r++) h->row_offset += cnt[r];
   return MIXDIR_B200_OK;
 }
@@ -1483,7 +1486,7 @@ static void layout_seg(const mixdir_b200_handle* h, int R, int G, bool fs, bool 
 // engine 5: k_em_seg.  Classes per CTA 16 or 32, 8 row groups per lane, tiles of at most 255 rows
 // (row numbers are bytes, 255 is the dummy).  MIXDIR_B200_FORCE_PLAN="KC,-,pairs,-,W" restricts
 // the search as for the unit kernel.
-static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
+static bool plan_seg_gs(const mixdir_b200_handle* h, Shard& s, int K, int gs, Plan* out) {
   if (h->CB != 1) return false;
   int fKC = -1, fRG = -1, fM = -1, fFPG = -1, fW = -1;
   if (const char* f = getenv("MIXDIR_B200_FORCE_PLAN"))
@@ -1495,8 +1498,10 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   // MIXDIR_B200_SEG_GLOBAL_STATS=1: no statistics table in shared memory, every (tile, feature, code)
   // sum goes to the global table with RED.ADD.U64.  That lets K = 32 run in ONE CTA (no cluster) and
   // K = 64, J = 100 in clusters of 4 x 16 classes -- both measured SLOWER than the default plans
-  // (DESIGN.md section 8), so the variant stays an A/B switch and is never chosen automatically.
-  const bool force_gs = getenv("MIXDIR_B200_SEG_GLOBAL_STATS") != nullptr;
+  // (DESIGN.md section 8).
+  // Automatic use: SMALL problems only, where the freed shared memory buys larger tiles and with them a
+  // whole round of tiles less (BASELINE configs[2], 70k x 60, K = 10: 160-row tiles in 3 rounds -> 240-row
+  // tiles in 2, E+M pass 106 -> 94 us), see plan_seg.
   const int kcs[2] = {32, 16};
   for (int KC : kcs) {
     if (fKC > 0 && KC != fKC) continue;
@@ -1509,7 +1514,7 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
       if (fW > 0 && W != fW) continue;
       const int R = W * RG * RPW;
       if (R > kSegDummyRow) continue;
-     for (int gs = force_gs ? 1 : 0; gs <= (force_gs ? 1 : 0); gs++) {
+     {
       Plan c;
       const bool fs = KC == 16 && P == 2 && !getenv("MIXDIR_B200_NO_FEATURE_SPLIT");
       // warp-specialised kernel (seg_ws.cuh): 16 M-step warps next to the W E-step warps
@@ -1561,6 +1566,28 @@ static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   }
   if (best.engine != 5) return false;
   *out = best;
+  return true;
+}
+
+// rounds of tiles ONE GPU's persistent grid would walk over ALL rows under a plan.  Deliberately not per
+// shard: the plan must not depend on the number of GPUs, or a fit on N GPUs would add its logit terms in
+// another order (another pair plan) than on one and lose its bit-identity with it.
+static int64_t seg_rounds(const mixdir_b200_handle* h, const Plan& p) {
+  const int64_t total = h->n_rows_global > 0 ? h->n_rows_global : h->n_rows * (int64_t)h->world;
+  const int64_t tiles = (total + p.R - 1) / p.R;
+  return (tiles + p.n_clusters - 1) / std::max(p.n_clusters, 1);
+}
+
+static bool plan_seg(const mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
+  if (getenv("MIXDIR_B200_SEG_GLOBAL_STATS")) return plan_seg_gs(h, s, K, 1, out);  // A/B switch
+  Plan a;
+  if (!plan_seg_gs(h, s, K, 0, &a)) return false;
+  *out = a;
+  const int64_t ra = seg_rounds(h, a);
+  if (ra <= 4 && !getenv("MIXDIR_B200_SEG_NO_GLOBAL_STATS")) {  // a small problem: would larger tiles save a round?
+    Plan b;
+    if (plan_seg_gs(h, s, K, 1, &b) && b.KC == a.KC && b.P == a.P && seg_rounds(h, b) < ra) *out = b;
+  }
   return true;
 }
 
@@ -1656,7 +1683,8 @@ static int plan_engine(mixdir_b200_handle* h, Shard& s, int K, Plan* out) {
   // to 32 bits can cost more than 1e-9 of the ELBO (seg.cuh), and such fits are launch-bound anyway.
   // MIXDIR_B200_FP64_STATS=1 keeps fp64 statistics (unit kernel) in automatic mode.
   static const bool fp64_stats = getenv("MIXDIR_B200_FP64_STATS") != nullptr;
-  const bool seg_ok = pref == 5 || (!fp64_stats && h->n_rows * (int64_t)h->world >= 16384);
+  const int64_t total_rows = h->n_rows_global > 0 ? h->n_rows_global : h->n_rows * (int64_t)h->world;
+  const bool seg_ok = pref == 5 || (!fp64_stats && total_rows >= 16384);
   if ((pref == 0 || pref == 5) && seg_ok && plan_seg(h, s, K, out)) return MIXDIR_B200_OK;
   if (pref == 5)
     return fail(MIXDIR_B200_BAD_ARGUMENT, "segment kernel does not fit this problem shape (K, sum C_j) "
