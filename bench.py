@@ -515,7 +515,11 @@ def run_ours(args):
         "records": records,
         "parity_vs_single": parity,
         "elbo_last": float(res["convergence"][-1]),
+        # host wall clock around the WHOLE value leg -- handle creation, the 0.6 GB upload and its scan, packing
+        # the unit codes and segment lists, W warm-up iterations, the K timed iterations, destroy -- over K;
+        # ms_per_step is the device time of the K timed iterations alone (CUDA events inside the engine)
         "wall_ms_per_step": (t1 - t0) * 1e3 / args.steps,
+        "wall_ms_per_step_covers": "create + upload + pack + warm-up + K iterations + destroy, divided by K",
     }
     print(json.dumps(line))
     if world > 1:
